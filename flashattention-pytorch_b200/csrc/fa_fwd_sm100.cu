@@ -1,0 +1,443 @@
+// Fused attention forward for sm_100a: TMA -> SMEM ring -> tcgen05.mma (S and O accumulators in TMEM) ->
+// register softmax (one thread per query row) -> P back to TMEM as the A operand of the P*V MMA.
+//
+// Replaces the reference's host-side ATen tile loops fa{1,2,3}_forward (csrc/fa1/fa1_fwd.cu:30-107; algorithmic
+// twin src/fa1/torch/impl.py:26-68): per query tile, stream KV tiles, online softmax with running max m and sum l,
+// O = sum_j e^{S_j - m} V_j, finally O / l and lse = m + log l.
+//
+// CTA = two 128-row query tiles (ping-pong) of one (batch*head) slice.
+//   warps 0-3  : softmax warpgroup for query tile 0 (thread t owns row t: TMEM lane == row, no shuffles)
+//   warps 4-7  : softmax warpgroup for query tile 1
+//   warp  8    : TMA producer (Q once, then K_0 V_0 K_1 V_1 ... through an NS-deep ring)
+//   warp  9    : MMA issuer (one lane), owns the TMEM allocation
+// TMEM (512 columns x 128 lanes, fp32):  [0,128) S0   [128,256) S1   [256,256+D) O0   [256+D,256+2D) O1
+//   P_i (16-bit) overwrites columns [0,64) of S_i and is consumed straight from TMEM (tcgen05.mma A-in-TMEM).
+// The tensor pipe executes MMAs in issue order, so "P_i V_j ; Q_i K_{j+1}^T" needs no barrier in between even though
+// S_i(j+1) overwrites P_i(j); while it runs, the other warpgroup does its softmax.
+#include "ptx.cuh"
+#include "fa_host.cuh"
+
+namespace fa {
+
+struct FwdParams {
+  float* lse;
+  const void* o_prev;
+  const float* lse_prev;
+  long long lse_bh_stride;
+  long long o_bh_stride;  // elements; o_prev shares o's geometry
+  int n_q, n_kv, bh, causal, diag, npairs;
+  float scale_log2;  // softmax_scale * log2(e)
+};
+
+constexpr int kBM = 128;  // query rows per tile
+constexpr int kBN = 128;  // key rows per tile
+constexpr int kFwdThreads = 320;
+constexpr float kRescaleThreshold = 8.0f;  // lazy O rescale: only when the row max grows by > 2^8
+
+template <int D>
+struct FwdCfg {
+  static constexpr int kStages = (D == 128) ? 4 : 8;
+  static constexpr int kTileBytes = 128 * D * 2;  // one Q / K / V tile
+  static constexpr int kSubTileBytes = 128 * 128;  // one 64-column (128-byte) swizzled sub-tile
+  static constexpr int kSmemBytes = 2 * kTileBytes + kStages * kTileBytes + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+// number of KV tiles a query tile starting at local row `row0` must visit
+__device__ __forceinline__ int fwd_num_kv_tiles(int row0, const FwdParams& p) {
+  if (row0 >= p.n_q) return 0;
+  int n = (p.n_kv + kBN - 1) / kBN;
+  if (p.causal) {
+    const long long last_visible = static_cast<long long>(row0) + kBM - 1 + p.diag;  // for the tile's last row
+    if (last_visible < 0) return 0;
+    const int nc = static_cast<int>(last_visible / kBN) + 1;
+    n = nc < n ? nc : n;
+  }
+  return n;
+}
+
+template <int D, bool kBF16>
+__global__ void __launch_bounds__(kFwdThreads, 1)
+fa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
+              const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_o, const FwdParams p) {
+  using Cfg = FwdCfg<D>;
+  constexpr int NS = Cfg::kStages;
+  constexpr int kSub = Cfg::kSubTileBytes;
+  constexpr int kChunks = D / 64;  // 64-column TMA boxes per tile row
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* q_smem = smem;                            // 2 tiles
+  uint8_t* kv_smem = smem + 2 * Cfg::kTileBytes;     // NS tiles
+  uint64_t* bars = reinterpret_cast<uint64_t*>(kv_smem + NS * Cfg::kTileBytes);
+  uint64_t* q_full = bars;            // [2]
+  uint64_t* s_full = bars + 2;        // [2]  MMA -> softmax: S_i(j) is in TMEM
+  uint64_t* p_ready = bars + 4;       // [2]  softmax -> MMA: P_i(j) stored (and O_i rescaled)
+  uint64_t* pv_done = bars + 6;       // [2]  MMA -> softmax: O_i += P_i(j) V_j finished
+  uint64_t* kv_full = bars + 8;       // [NS]
+  uint64_t* kv_empty = bars + 8 + NS; // [NS]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8 + 2 * NS);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // heavy (late, for causal) tile pairs first; all pairs of one slice adjacent so its K/V stay L2-resident
+  const int bh = blockIdx.x / p.npairs;
+  const int pair = p.npairs - 1 - (blockIdx.x % p.npairs);
+  const int row0_t0 = pair * 2 * kBM;
+  const int nt0 = fwd_num_kv_tiles(row0_t0, p);
+  const int nt1 = fwd_num_kv_tiles(row0_t0 + kBM, p);
+  const int ntmax = nt0 > nt1 ? nt0 : nt1;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&q_full[i], 1);
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_ready[i], 128);
+      mbar_init(&pv_done[i], 1);
+    }
+    for (int i = 0; i < NS; ++i) {
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 8 && lane == 0) {
+    tma_prefetch_desc(&tm_q);
+    tma_prefetch_desc(&tm_k);
+    tma_prefetch_desc(&tm_v);
+    tma_prefetch_desc(&tm_o);
+  }
+  if (warp == 9) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 8) {
+    // ===================================== TMA producer =====================================
+    if (lane == 0) {
+      for (int i = 0; i < 2; ++i) {
+        mbar_arrive_expect_tx(&q_full[i], Cfg::kTileBytes);
+        for (int c = 0; c < kChunks; ++c)
+          tma_load_3d(q_smem + i * Cfg::kTileBytes + c * kSub, &tm_q, &q_full[i], c * 64, row0_t0 + i * kBM, bh);
+      }
+      for (int t = 0; t < 2 * ntmax; ++t) {
+        const int stage = t % NS;
+        mbar_wait(&kv_empty[stage], ((t / NS) & 1) ^ 1);
+        mbar_arrive_expect_tx(&kv_full[stage], Cfg::kTileBytes);
+        const CUtensorMap* tm = (t & 1) ? &tm_v : &tm_k;
+        for (int c = 0; c < kChunks; ++c)
+          tma_load_3d(kv_smem + stage * Cfg::kTileBytes + c * kSub, tm, &kv_full[stage], c * 64, (t >> 1) * kBN, bh);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 9) {
+    // ===================================== MMA issuer =====================================
+    if (lane == 0 && ntmax > 0) {
+      constexpr uint32_t idesc_s = umma_idesc(kBF16, kBM, kBN, false, false);  // S = Q K^T : A, B K-major
+      constexpr uint32_t idesc_o = umma_idesc(kBF16, kBM, D, false, true);     // O += P V : A in TMEM, B MN-major
+      const uint32_t q_addr = smem_u32(q_smem);
+      const uint32_t kv_addr = smem_u32(kv_smem);
+      const int nt[2] = {nt0, nt1};
+
+      auto issue_s = [&](int i, int stage) {
+        const uint32_t a0 = q_addr + i * Cfg::kTileBytes;
+        const uint32_t b0 = kv_addr + stage * Cfg::kTileBytes;
+#pragma unroll
+        for (int kk = 0; kk < D / 16; ++kk) {
+          const uint32_t off = (kk >> 2) * kSub + (kk & 3) * 32;  // 16 elements = 32 B inside the 128-B swizzle row
+          umma_ss(tmem_base + i * kBN, umma_smem_desc(a0 + off, 16, 1024), umma_smem_desc(b0 + off, 16, 1024),
+                  idesc_s, kk > 0 ? 1u : 0u);
+        }
+      };
+      auto issue_pv = [&](int i, int stage, bool acc) {
+        const uint32_t b0 = kv_addr + stage * Cfg::kTileBytes;
+#pragma unroll
+        for (int kk = 0; kk < kBN / 16; ++kk) {
+          // A: 16 key columns of P = 8 TMEM columns (two 16-bit values per column).  B: 16 key rows of V.
+          umma_ts(tmem_base + 256 + i * D, tmem_base + i * kBN + kk * 8,
+                  umma_smem_desc(b0 + kk * 16 * 128, kSub, 1024), idesc_o, (acc || kk > 0) ? 1u : 0u);
+        }
+      };
+      auto stage_of = [&](int t) { return t % NS; };
+      auto phase_of = [&](int t) { return (t / NS) & 1; };
+
+      mbar_wait(&q_full[0], 0);
+      mbar_wait(&q_full[1], 0);
+      mbar_wait(&kv_full[stage_of(0)], phase_of(0));
+      tc_fence_after();
+      for (int i = 0; i < 2; ++i) {
+        if (nt[i] > 0) {
+          issue_s(i, stage_of(0));
+          tc_commit(&s_full[i]);
+        }
+      }
+      tc_commit(&kv_empty[stage_of(0)]);
+
+      for (int j = 0; j < ntmax; ++j) {
+        const int tv = 2 * j + 1, tk = 2 * j + 2;
+        const bool has_next = (j + 1 < ntmax);
+        mbar_wait(&kv_full[stage_of(tv)], phase_of(tv));
+        bool k_ready = false;
+        for (int i = 0; i < 2; ++i) {
+          if (j < nt[i]) {
+            mbar_wait(&p_ready[i], j & 1);
+            tc_fence_after();
+            issue_pv(i, stage_of(tv), j > 0);
+            tc_commit(&pv_done[i]);
+          }
+          if (j + 1 < nt[i]) {
+            if (!k_ready) {
+              mbar_wait(&kv_full[stage_of(tk)], phase_of(tk));
+              tc_fence_after();
+              k_ready = true;
+            }
+            issue_s(i, stage_of(tk));
+            tc_commit(&s_full[i]);
+          }
+        }
+        tc_commit(&kv_empty[stage_of(tv)]);
+        if (has_next) {
+          if (!k_ready) mbar_wait(&kv_full[stage_of(tk)], phase_of(tk));
+          tc_commit(&kv_empty[stage_of(tk)]);
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================================== softmax warpgroups =====================================
+    const int wg = warp >> 2;            // query tile 0 / 1
+    const int row = threadIdx.x & 127;   // row inside the tile == TMEM lane
+    const int nt = wg == 0 ? nt0 : nt1;
+    const int tile_row0 = row0_t0 + wg * kBM;
+    const int row_l = tile_row0 + row;   // row inside this slice
+    const uint32_t lane_sel = static_cast<uint32_t>((warp & 3) * 32) << 16;
+    const uint32_t t_s = tmem_base + lane_sel + wg * kBN;
+    const uint32_t t_o = tmem_base + lane_sel + 256 + wg * D;
+    const float c = p.scale_log2;
+    // largest visible key index for this row, in slice-local coordinates
+    long long vis = p.n_kv - 1;
+    if (p.causal) {
+      const long long cv = static_cast<long long>(row_l) + p.diag;
+      vis = cv < vis ? cv : vis;
+    }
+
+    float m_ref = -INFINITY;  // reference max (raw score units) all stored exponentials are relative to
+    float l_sum = 0.f;
+
+    for (int j = 0; j < nt; ++j) {
+      mbar_wait(&s_full[wg], j & 1);
+      tc_fence_after();
+      float s[kBN];
+#pragma unroll
+      for (int q4 = 0; q4 < kBN / 32; ++q4) tmem_ld32(t_s + q4 * 32, reinterpret_cast<uint32_t*>(s) + q4 * 32);
+      tc_wait_ld();
+
+      const long long lim_ll = vis - static_cast<long long>(j) * kBN;
+      if (lim_ll < kBN - 1) {
+        const int lim = lim_ll < -1 ? -1 : static_cast<int>(lim_ll);
+#pragma unroll
+        for (int x = 0; x < kBN; ++x) s[x] = (x > lim) ? -INFINITY : s[x];
+      }
+
+      float mx0 = s[0], mx1 = s[1], mx2 = s[2], mx3 = s[3];
+#pragma unroll
+      for (int x = 4; x < kBN; x += 4) {
+        mx0 = fmaxf(mx0, s[x]);
+        mx1 = fmaxf(mx1, s[x + 1]);
+        mx2 = fmaxf(mx2, s[x + 2]);
+        mx3 = fmaxf(mx3, s[x + 3]);
+      }
+      const float m_tile = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+      const float m_new = fmaxf(m_ref, m_tile);
+
+      bool rescale = false;
+      float alpha = 1.f;
+      if (j == 0) {
+        m_ref = m_new;
+      } else {
+        const bool need = (m_new - m_ref) * c > kRescaleThreshold;  // (-inf -> finite) is "needed"; NaN is not
+        if (__any_sync(0xffffffffu, need)) {
+          const float m_safe = (m_new == -INFINITY) ? 0.f : m_new;
+          alpha = ex2((m_ref - m_safe) * c);
+          l_sum *= alpha;
+          m_ref = m_new;
+          rescale = true;
+        }
+      }
+      const float mc = ((m_ref == -INFINITY) ? 0.f : m_ref) * c;
+
+      // P = 2^(S*c - m*c), row-sum in fp32, stored 16-bit into the first 64 columns of S
+      float ls0 = 0.f, ls1 = 0.f;
+#pragma unroll
+      for (int q2 = 0; q2 < kBN / 32; ++q2) {
+        uint32_t pk[16];
+#pragma unroll
+        for (int x = 0; x < 16; ++x) {
+          const float p0 = ex2(fmaf(s[q2 * 32 + 2 * x], c, -mc));
+          const float p1 = ex2(fmaf(s[q2 * 32 + 2 * x + 1], c, -mc));
+          ls0 += p0;
+          ls1 += p1;
+          pk[x] = pack2<kBF16>(p0, p1);
+        }
+        tmem_st16(t_s + q2 * 16, pk);
+      }
+      l_sum += ls0 + ls1;
+
+      if (rescale) {  // warp-uniform
+        mbar_wait(&pv_done[wg], (j - 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int q4 = 0; q4 < D / 32; ++q4) {
+          float o[32];
+          tmem_ld32(t_o + q4 * 32, reinterpret_cast<uint32_t*>(o));
+          tc_wait_ld();
+#pragma unroll
+          for (int x = 0; x < 32; ++x) o[x] *= alpha;
+          tmem_st32(t_o + q4 * 32, reinterpret_cast<const uint32_t*>(o));
+        }
+      }
+      tc_wait_st();
+      tc_fence_before();
+      mbar_arrive(&p_ready[wg]);
+    }
+
+    // ------------------------------- epilogue: O / l, lse, optional LSE merge, TMA store -------------------------------
+    if (nt > 0) {
+      mbar_wait(&pv_done[wg], (nt - 1) & 1);
+      tc_fence_after();
+    } else {
+      mbar_wait(&q_full[wg], 0);  // the Q buffer doubles as the O staging tile: its TMA load must have landed
+    }
+    const bool has_mass = l_sum > 0.f;
+    float w_cur = has_mass ? 1.f / l_sum : 0.f;
+    const float m_fin = (m_ref == -INFINITY) ? 0.f : m_ref;
+    float lse_val = has_mass ? (m_fin * c + log2f(l_sum)) * 0.6931471805599453f : -INFINITY;
+    float w_prev = 0.f;
+    const bool merge = (p.lse_prev != nullptr) && (row_l < p.n_q);
+    if (merge) {
+      const float lp = p.lse_prev[static_cast<long long>(bh) * p.lse_bh_stride + row_l];
+      const float hi = fmaxf(lp, lse_val);
+      if (hi == -INFINITY) {
+        w_prev = 0.f;
+        w_cur = 0.f;
+      } else {
+        const float e_prev = __expf(lp - hi), e_cur = __expf(lse_val - hi);
+        const float tot = e_prev + e_cur;
+        w_prev = e_prev / tot;
+        w_cur *= e_cur / tot;
+        lse_val = hi + __logf(tot);
+      }
+    }
+    uint8_t* stage_tile = q_smem + wg * Cfg::kTileBytes;
+    const uint32_t* o_prev_row =
+        merge ? reinterpret_cast<const uint32_t*>(static_cast<const uint16_t*>(p.o_prev) +
+                                                  static_cast<long long>(bh) * p.o_bh_stride +
+                                                  static_cast<long long>(row_l) * D)
+              : nullptr;
+#pragma unroll
+    for (int q4 = 0; q4 < D / 32; ++q4) {
+      float o[32];
+      if (nt > 0) {
+        tmem_ld32(t_o + q4 * 32, reinterpret_cast<uint32_t*>(o));
+        tc_wait_ld();
+      } else {
+#pragma unroll
+        for (int x = 0; x < 32; ++x) o[x] = 0.f;
+      }
+      uint32_t pk[16];
+#pragma unroll
+      for (int x = 0; x < 16; ++x) {
+        float a = o[2 * x] * w_cur, b = o[2 * x + 1] * w_cur;
+        if (merge) {
+          const float2 pv = unpack2<kBF16>(o_prev_row[q4 * 16 + x]);
+          a = fmaf(pv.x, w_prev, a);
+          b = fmaf(pv.y, w_prev, b);
+        }
+        pk[x] = pack2<kBF16>(a, b);
+      }
+      // 32 columns = 64 B = four 16-byte chunks of the 128-byte swizzled row
+      uint8_t* sub = stage_tile + (q4 >> 1) * kSub + row * 128;
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch) {
+        const int chunk = (q4 & 1) * 4 + ch;
+        *reinterpret_cast<uint4*>(sub + ((chunk ^ (row & 7)) << 4)) =
+            make_uint4(pk[4 * ch], pk[4 * ch + 1], pk[4 * ch + 2], pk[4 * ch + 3]);
+      }
+    }
+    if (row_l < p.n_q) p.lse[static_cast<long long>(bh) * p.lse_bh_stride + row_l] = lse_val;
+    fence_proxy_async_smem();
+    named_bar_sync(1 + wg, 128);
+    if (row == 0 && tile_row0 < p.n_q) {
+      for (int ch = 0; ch < kChunks; ++ch) tma_store_3d(&tm_o, stage_tile + ch * kSub, ch * 64, tile_row0, bh);
+      tma_store_commit();
+      tma_store_wait_all<0>();
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) tmem_dealloc(tmem_base, 512);
+}
+
+template <int D, bool kBF16>
+static int launch_fwd(const Geometry& g, const void* q, const void* k, const void* v, void* o, float* lse,
+                      const void* o_prev, const float* lse_prev, cudaStream_t stream) {
+  using Cfg = FwdCfg<D>;
+  const int elem = kBF16 ? kElemBF16 : kElemF16;
+  CUtensorMap tm_q, tm_k, tm_v, tm_o;
+  int rc;
+  if ((rc = make_tmap_3d(&tm_q, q, elem, D, g.n_q, g.bh, g.q_bh_stride, 64, kBM))) return rc;
+  if ((rc = make_tmap_3d(&tm_k, k, elem, D, g.n_kv, g.bh, g.kv_bh_stride, 64, kBN))) return rc;
+  if ((rc = make_tmap_3d(&tm_v, v, elem, D, g.n_kv, g.bh, g.kv_bh_stride, 64, kBN))) return rc;
+  if ((rc = make_tmap_3d(&tm_o, o, elem, D, g.n_q, g.bh, g.q_bh_stride, 64, kBM))) return rc;
+
+  FwdParams p;
+  p.lse = lse;
+  p.o_prev = o_prev;
+  p.lse_prev = lse_prev;
+  p.lse_bh_stride = g.lse_bh_stride;
+  p.o_bh_stride = g.q_bh_stride;
+  p.n_q = static_cast<int>(g.n_q);
+  p.n_kv = static_cast<int>(g.n_kv);
+  p.bh = static_cast<int>(g.bh);
+  p.causal = g.causal;
+  p.diag = g.diag;
+  p.npairs = static_cast<int>((g.n_q + 2 * kBM - 1) / (2 * kBM));
+  p.scale_log2 = g.scale * 1.4426950408889634f;
+
+  auto kern = fa_fwd_kernel<D, kBF16>;
+  static bool attr_set = false;  // benign race: idempotent
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes) != cudaSuccess)
+      return FA_SM100_ELAUNCH;
+    attr_set = true;
+  }
+  const long long nblocks = static_cast<long long>(p.npairs) * g.bh;
+  if (nblocks > 0x7fffffffll) return FA_SM100_EINVAL_SHAPE;
+  kern<<<static_cast<unsigned>(nblocks), kFwdThreads, Cfg::kSmemBytes, stream>>>(tm_q, tm_k, tm_v, tm_o, p);
+  return launch_status();
+}
+
+}  // namespace fa
+
+extern "C" int fa_sm100_fwd(const fa_sm100_shape* s, const void* q, const void* k, const void* v, void* o,
+                            float* lse, const void* o_prev, const float* lse_prev, void* stream) {
+  fa::Geometry g;
+  int rc = fa::check_shape(s, &g);
+  if (rc) return rc;
+  if (!fa::aligned16(q) || !fa::aligned16(k) || !fa::aligned16(v) || !fa::aligned16(o) || lse == nullptr)
+    return FA_SM100_EINVAL_PTR;
+  if ((o_prev == nullptr) != (lse_prev == nullptr)) return FA_SM100_EINVAL_PTR;
+  if ((rc = fa::check_device())) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (g.d == 128) {
+    return g.dtype == FA_SM100_DTYPE_BF16 ? fa::launch_fwd<128, true>(g, q, k, v, o, lse, o_prev, lse_prev, st)
+                                          : fa::launch_fwd<128, false>(g, q, k, v, o, lse, o_prev, lse_prev, st);
+  }
+  return g.dtype == FA_SM100_DTYPE_BF16 ? fa::launch_fwd<64, true>(g, q, k, v, o, lse, o_prev, lse_prev, st)
+                                        : fa::launch_fwd<64, false>(g, q, k, v, o, lse, o_prev, lse_prev, st);
+}

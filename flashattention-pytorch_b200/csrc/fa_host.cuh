@@ -1,0 +1,97 @@
+// Host-side helpers shared by the C-ABI entry points: TMA tensor-map encoding through the driver entry point
+// (no -lcuda link: the library must build and load on a GPU-less box), argument validation, error codes.
+#pragma once
+#include <cuda.h>
+#include <cudaTypedefs.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cmath>
+#include <mutex>
+
+#include "../../include/fa_sm100.h"
+
+namespace fa {
+
+enum : int { kElemF16 = 0, kElemBF16 = 1, kElemF32 = 2 };
+
+inline PFN_cuTensorMapEncodeTiled_v12000 tensor_map_encoder() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess) {
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+    }
+  });
+  return fn;
+}
+
+// 3-D tensor (cols, rows, slices) over a dense-row tensor; box = (box_cols, box_rows, 1).
+// 128-byte swizzle when box_cols * elem_size == 128, which is what every UMMA operand tile here uses.
+inline int make_tmap_3d(CUtensorMap* out, const void* ptr, int elem, uint64_t cols, uint64_t rows, uint64_t slices,
+                        uint64_t slice_stride_elems, uint32_t box_cols, uint32_t box_rows) {
+  auto enc = tensor_map_encoder();
+  if (!enc) return FA_SM100_EDRIVER;
+  const uint64_t esz = (elem == kElemF32) ? 4 : 2;
+  CUtensorMapDataType dt = elem == kElemF32   ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                           : elem == kElemBF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+                                               : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  cuuint64_t gdim[3] = {cols, rows, slices};
+  cuuint64_t gstride[2] = {cols * esz, slice_stride_elems * esz};
+  cuuint32_t box[3] = {box_cols, box_rows, 1};
+  cuuint32_t estride[3] = {1, 1, 1};
+  CUtensorMapSwizzle sw = (box_cols * esz == 128) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE;
+  CUresult r = enc(out, dt, 3, const_cast<void*>(ptr), gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? FA_SM100_OK : FA_SM100_EDRIVER;
+}
+
+inline bool aligned16(const void* p) { return p != nullptr && (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+struct Geometry {
+  long long bh, n_q, n_kv, q_bh_stride, kv_bh_stride, lse_bh_stride;
+  int d, dtype, causal, diag;  // diag = q_row0 - kv_col0: key c visible to query r iff c <= r + diag
+  float scale;
+};
+
+inline int check_shape(const fa_sm100_shape* s, Geometry* g) {
+  if (!s) return FA_SM100_EINVAL_PTR;
+  if (s->dtype != FA_SM100_DTYPE_F16 && s->dtype != FA_SM100_DTYPE_BF16) return FA_SM100_EINVAL_DTYPE;
+  if (s->d != 64 && s->d != 128) return FA_SM100_EINVAL_HEADDIM;
+  if (s->bh <= 0 || s->n_q <= 0 || s->n_kv <= 0) return FA_SM100_EINVAL_SHAPE;
+  if (s->n_q > (1ll << 30) || s->n_kv > (1ll << 30) || s->bh > (1ll << 30)) return FA_SM100_EINVAL_SHAPE;
+  if (!(s->softmax_scale > 0.f) || !std::isfinite(s->softmax_scale)) return FA_SM100_EINVAL_SCALE;
+  const long long diag = s->q_row0 - s->kv_col0;
+  if (diag > (1ll << 30) || diag < -(1ll << 30)) return FA_SM100_EINVAL_SHAPE;
+  g->bh = s->bh;
+  g->n_q = s->n_q;
+  g->n_kv = s->n_kv;
+  g->d = s->d;
+  g->dtype = s->dtype;
+  g->causal = s->causal ? 1 : 0;
+  g->diag = static_cast<int>(diag);
+  g->scale = s->softmax_scale;
+  g->q_bh_stride = s->q_bh_stride ? s->q_bh_stride : s->n_q * s->d;
+  g->kv_bh_stride = s->kv_bh_stride ? s->kv_bh_stride : s->n_kv * s->d;
+  g->lse_bh_stride = s->lse_bh_stride ? s->lse_bh_stride : s->n_q;
+  if (g->q_bh_stride < s->n_q * s->d || g->kv_bh_stride < s->n_kv * s->d || g->lse_bh_stride < s->n_q)
+    return FA_SM100_EINVAL_SHAPE;
+  if ((g->q_bh_stride % 8) || (g->kv_bh_stride % 8)) return FA_SM100_EINVAL_SHAPE;  // TMA: 16-byte strides
+  return FA_SM100_OK;
+}
+
+inline int check_device() {
+  static int cached = 1;  // 1 = unknown
+  if (cached != 1) return cached;
+  int dev = 0, major = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return FA_SM100_EDEVICE;
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return FA_SM100_EDEVICE;
+  cached = (major == 10) ? FA_SM100_OK : FA_SM100_EDEVICE;
+  return cached;
+}
+
+inline int launch_status() { return cudaGetLastError() == cudaSuccess ? FA_SM100_OK : FA_SM100_ELAUNCH; }
+
+}  // namespace fa

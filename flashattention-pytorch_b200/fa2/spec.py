@@ -1,0 +1,16 @@
+"""Tile spec of the FA2 entry point — same dataclass and values as the reference (``src/fa2/spec.py``).
+
+The values travel through the extension ABI unchanged (``br``, ``bc``); the sm_100a kernel ignores them and uses its
+own tcgen05 shapes (128-row query tiles, 128-row KV tiles), which does not change the result beyond rounding."""
+from dataclasses import dataclass
+
+
+@dataclass(frozen=True)
+class FA2Spec:
+    br: int
+    bc: int
+    num_warps: int
+
+
+def pick_fa2_spec(head_dim: int) -> FA2Spec:
+    return FA2Spec(br=128, bc=128, num_warps=8) if head_dim <= 64 else FA2Spec(br=64, bc=128, num_warps=8)

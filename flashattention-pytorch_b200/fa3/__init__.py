@@ -1,0 +1,2 @@
+from .op import fa3_attention  # noqa: F401
+from .spec import FA3Spec, pick_fa3_spec  # noqa: F401

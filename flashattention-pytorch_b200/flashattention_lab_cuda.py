@@ -1,0 +1,305 @@
+"""``flashattention_lab_cuda`` — the module name the reference's CUDA wrappers import
+(reference ``src/fa2/cuda/impl.py:6-16``), re-implemented as a thin ctypes shim over the hand-written sm_100a
+library ``libfa_sm100.so`` (C ABI in ``include/fa_sm100.h``).
+
+It exports exactly the six functions of the reference's pybind module
+(reference ``csrc/common/torch.extension.cpp:73-83``) with the same positional arguments and return tuples:
+
+    fa1_forward / forward / fa3_forward      (q, k, v, causal, softmax_scale, br, bc[, stages, fp8]) -> (o, lse)
+    fa1_backward / backward / fa3_backward   (q, k, v, o, do, lse, causal, softmax_scale, br, bc[, stages, fp8])
+                                             -> (dq, dk, dv)
+
+Deliberate deviations from the reference (see DESIGN.md "Deviations"):
+  * ``forward`` (FA2) returns the correctly normalised O; the reference divides by the row sum twice
+    (reference ``csrc/fa2/fa2_fwd.cu:92-93,99``).
+  * the backward uses the causal block rule of the Python twin (reference ``src/fa1/torch/impl.py:89``), not the
+    inverted test in ``csrc/fa1/fa1_bwd.cu:80``.
+  * ``br``/``bc``/``stages`` are accepted and ignored: the kernel picks its own tcgen05 tile shapes and the result
+    does not depend on them beyond rounding.
+  * fp32 inputs and ``fp8=True`` are rejected loudly (the reference's fp8 emulation is broken).
+
+There is NO fallback: if the shared library is missing or the device is not sm_100 every call raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from pathlib import Path
+
+import torch
+
+_HERE = Path(__file__).resolve().parent
+_LIB_NAME = "libfa_sm100.so"
+_lib = None
+
+
+class _Shape(ctypes.Structure):
+    """Mirror of ``fa_sm100_shape`` (include/fa_sm100.h)."""
+
+    _fields_ = [
+        ("bh", ctypes.c_int64),
+        ("n_q", ctypes.c_int64),
+        ("n_kv", ctypes.c_int64),
+        ("d", ctypes.c_int32),
+        ("dtype", ctypes.c_int32),
+        ("causal", ctypes.c_int32),
+        ("softmax_scale", ctypes.c_float),
+        ("q_row0", ctypes.c_int64),
+        ("kv_col0", ctypes.c_int64),
+        ("q_bh_stride", ctypes.c_int64),
+        ("kv_bh_stride", ctypes.c_int64),
+        ("lse_bh_stride", ctypes.c_int64),
+    ]
+
+
+# every symbol include/fa_sm100.h declares: name -> (restype, argtypes)
+_P = ctypes.c_void_p
+_SP = ctypes.POINTER(_Shape)
+ABI = {
+    "fa_sm100_version": (ctypes.c_int, []),
+    "fa_sm100_strerror": (ctypes.c_char_p, [ctypes.c_int]),
+    "fa_sm100_dq_accum_bytes": (ctypes.c_size_t, [_SP]),
+    "fa_sm100_fwd": (ctypes.c_int, [_SP, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "fa_sm100_bwd_delta": (ctypes.c_int, [_SP, _P, _P, _P, _P]),
+    "fa_sm100_bwd": (ctypes.c_int, [_SP, _P, _P, _P, _P, _P, _P, _P, _P, _P, ctypes.c_int, _P]),
+    "fa_sm100_dq_finish": (ctypes.c_int, [_SP, _P, _P, _P]),
+    "fa_sm100_cast_scaled": (ctypes.c_int, [_P, _P, ctypes.c_int64, ctypes.c_float, ctypes.c_int32, _P]),
+    "fa_sm100_probe_umma": (ctypes.c_int, [ctypes.c_int, ctypes.c_int32, _P, _P, _P, _P]),
+}
+
+
+def library_path() -> Path:
+    override = os.environ.get("FA_SM100_LIB")
+    return Path(override) if override else _HERE / _LIB_NAME
+
+
+def load_library():
+    """dlopen libfa_sm100.so and bind the C ABI.  Raises ImportError if it is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = library_path()
+    if not path.exists():
+        raise ImportError(
+            f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc -gencode arch=compute_100a,code=sm_100a). There is no CPU/Triton fallback on this path."
+        )
+    lib = ctypes.CDLL(str(path))
+    for name, (restype, argtypes) in ABI.items():
+        fn = getattr(lib, name)  # AttributeError if the library does not export what the header declares
+        fn.restype = restype
+        fn.argtypes = argtypes
+    if lib.fa_sm100_version() < 100:
+        raise ImportError("libfa_sm100.so is older than this shim")
+    _lib = lib
+    return lib
+
+
+def _check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load_library().fa_sm100_strerror(rc).decode()
+        raise RuntimeError(f"{what} failed: {msg} (code {rc})")
+
+
+_DTYPES = {torch.float16: 0, torch.bfloat16: 1}
+
+
+def _dtype_code(t: torch.Tensor) -> int:
+    try:
+        return _DTYPES[t.dtype]
+    except KeyError:
+        raise NotImplementedError(
+            f"flashattention_lab_cuda (sm_100a): dtype {t.dtype} is not supported; the tcgen05 path takes fp16/bf16"
+        ) from None
+
+
+def _padded_head_dim(d: int) -> int:
+    if d <= 64:
+        return 64
+    if d <= 128:
+        return 128
+    raise NotImplementedError(f"flashattention_lab_cuda (sm_100a): head dim {d} > 128 is not supported yet")
+
+
+def _pad_d(x: torch.Tensor, dp: int) -> torch.Tensor:
+    d = x.shape[-1]
+    if d == dp:
+        return x.contiguous()
+    return torch.nn.functional.pad(x, (0, dp - d)).contiguous()
+
+
+def _stream_ptr(t: torch.Tensor) -> int:
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _validate_qkv(q, k, v):
+    # reference csrc/fa2/fa2_fwd.cu:40-45 (TORCH_CHECK -> RuntimeError)
+    if q.dim() != 3 or k.dim() != 3 or v.dim() != 3:
+        raise RuntimeError("q, k, v must be 3-D (batch*heads, seqlen, head_dim)")
+    if q.shape != k.shape or q.shape != v.shape:
+        raise RuntimeError("q, k, v must have identical shapes")
+    if not (q.is_cuda and k.is_cuda and v.is_cuda):
+        raise RuntimeError("Inputs must be CUDA tensors")
+    if not (q.dtype == k.dtype == v.dtype):
+        raise RuntimeError("q, k, v must share one dtype")
+
+
+def make_shape(bh, n_q, n_kv, d, dtype_code, causal, softmax_scale, q_row0=0, kv_col0=0, q_bh_stride=0,
+               kv_bh_stride=0, lse_bh_stride=0) -> _Shape:
+    return _Shape(int(bh), int(n_q), int(n_kv), int(d), int(dtype_code), 1 if causal else 0, float(softmax_scale),
+                  int(q_row0), int(kv_col0), int(q_bh_stride), int(kv_bh_stride), int(lse_bh_stride))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# raw (already padded / contiguous) entry points — also used by the sharding and ring-attention drivers
+# ------------------------------------------------------------------------------------------------------------------
+def fwd_raw(q, k, v, causal, softmax_scale, *, q_row0=0, kv_col0=0, out=None, lse=None, merge=False):
+    """q: (bh, n_q, d), k/v: (bh, n_kv, d), d in {64,128}, contiguous.  Returns (o, lse).
+
+    ``merge=True`` folds the new partial into the given ``out``/``lse`` by log-sum-exp (ring attention)."""
+    lib = load_library()
+    bh, n_q, d = q.shape
+    n_kv = k.shape[1]
+    if out is None:
+        if merge:
+            raise ValueError("merge=True needs out/lse from the previous step")
+        out = torch.empty_like(q)
+        lse = torch.empty((bh, n_q), device=q.device, dtype=torch.float32)
+    shape = make_shape(bh, n_q, n_kv, d, _dtype_code(q), causal, softmax_scale, q_row0, kv_col0)
+    prev_o = out.data_ptr() if merge else None
+    prev_lse = lse.data_ptr() if merge else None
+    with torch.cuda.device(q.device):
+        rc = lib.fa_sm100_fwd(ctypes.byref(shape), q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(),
+                              lse.data_ptr(), prev_o, prev_lse, _stream_ptr(q))
+    _check(rc, "fa_sm100_fwd")
+    return out, lse
+
+
+def bwd_raw(q, k, v, o, do, lse, causal, softmax_scale, *, q_row0=0, kv_col0=0, delta=None, dq_accum=None,
+            dkv_accum=None):
+    """Backward on padded/contiguous tensors.
+
+    Plain call: returns (dq, dk, dv) in the input dtype.
+    Ring call (``dq_accum`` fp32 (bh,n_q,d) and ``dkv_accum`` = (dk32, dv32) given): accumulates into them and
+    returns None — the caller finishes with ``dq_finish_raw`` / ``cast_scaled`` once the ring has gone round."""
+    lib = load_library()
+    bh, n_q, d = q.shape
+    n_kv = k.shape[1]
+    shape = make_shape(bh, n_q, n_kv, d, _dtype_code(q), causal, softmax_scale, q_row0, kv_col0)
+    sp = ctypes.byref(shape)
+    stream = _stream_ptr(q)
+    with torch.cuda.device(q.device):
+        if delta is None:
+            delta = torch.empty((bh, n_q), device=q.device, dtype=torch.float32)
+            _check(lib.fa_sm100_bwd_delta(sp, o.data_ptr(), do.data_ptr(), delta.data_ptr(), stream),
+                   "fa_sm100_bwd_delta")
+        ring = dq_accum is not None
+        if not ring:
+            dq_accum = torch.zeros((bh, n_q, d), device=q.device, dtype=torch.float32)
+            dk = torch.empty_like(k)
+            dv = torch.empty_like(v)
+            acc_flag = 0
+        else:
+            dk, dv = dkv_accum
+            acc_flag = 1
+        _check(lib.fa_sm100_bwd(sp, q.data_ptr(), k.data_ptr(), v.data_ptr(), do.data_ptr(), lse.data_ptr(),
+                                delta.data_ptr(), dq_accum.data_ptr(), dk.data_ptr(), dv.data_ptr(), acc_flag,
+                                stream), "fa_sm100_bwd")
+        if ring:
+            return None
+        dq = torch.empty_like(q)
+        _check(lib.fa_sm100_dq_finish(sp, dq_accum.data_ptr(), dq.data_ptr(), stream), "fa_sm100_dq_finish")
+    return dq, dk, dv
+
+
+def delta_raw(o, do):
+    lib = load_library()
+    bh, n_q, d = o.shape
+    shape = make_shape(bh, n_q, n_q, d, _dtype_code(o), False, 1.0)
+    delta = torch.empty((bh, n_q), device=o.device, dtype=torch.float32)
+    with torch.cuda.device(o.device):
+        _check(lib.fa_sm100_bwd_delta(ctypes.byref(shape), o.data_ptr(), do.data_ptr(), delta.data_ptr(),
+                                      _stream_ptr(o)), "fa_sm100_bwd_delta")
+    return delta
+
+
+def cast_scaled(acc: torch.Tensor, alpha: float, dtype: torch.dtype) -> torch.Tensor:
+    lib = load_library()
+    out = torch.empty(acc.shape, device=acc.device, dtype=dtype)
+    with torch.cuda.device(acc.device):
+        _check(lib.fa_sm100_cast_scaled(acc.data_ptr(), out.data_ptr(), acc.numel(), float(alpha), _DTYPES[dtype],
+                                        _stream_ptr(acc)), "fa_sm100_cast_scaled")
+    return out
+
+
+def probe_umma(mode: int, a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    lib = load_library()
+    out = torch.empty((128, 128), device=a.device, dtype=torch.float32)
+    with torch.cuda.device(a.device):
+        _check(lib.fa_sm100_probe_umma(int(mode), _dtype_code(a), a.data_ptr(), b.data_ptr(), out.data_ptr(),
+                                       _stream_ptr(a)), "fa_sm100_probe_umma")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# the six functions of the reference's pybind module
+# ------------------------------------------------------------------------------------------------------------------
+@torch.no_grad()  # reference csrc/fa2/fa2_fwd.cu:38 (NoGradGuard)
+def _forward(q, k, v, causal, softmax_scale):
+    _validate_qkv(q, k, v)
+    d = q.shape[-1]
+    dp = _padded_head_dim(d)
+    o, lse = fwd_raw(_pad_d(q, dp), _pad_d(k, dp), _pad_d(v, dp), bool(causal), float(softmax_scale))
+    if dp != d:
+        o = o[..., :d].contiguous()
+    return o, lse
+
+
+@torch.no_grad()
+def _backward(q, k, v, o, do, lse, causal, softmax_scale):
+    _validate_qkv(q, k, v)
+    if o.shape != q.shape or do.shape != q.shape:
+        raise RuntimeError("o and do must have q's shape")
+    if lse.shape != q.shape[:2]:
+        raise RuntimeError("lse must be (batch*heads, seqlen)")
+    d = q.shape[-1]
+    dp = _padded_head_dim(d)
+    dq, dk, dv = bwd_raw(_pad_d(q, dp), _pad_d(k, dp), _pad_d(v, dp), _pad_d(o, dp), _pad_d(do.to(q.dtype), dp),
+                         lse.to(torch.float32).contiguous(), bool(causal), float(softmax_scale))
+    if dp != d:
+        dq, dk, dv = (t[..., :d].contiguous() for t in (dq, dk, dv))
+    return dq, dk, dv
+
+
+def fa1_forward(q, k, v, causal, softmax_scale, br, bc):
+    return _forward(q, k, v, causal, softmax_scale)
+
+
+def fa1_backward(q, k, v, o, do, lse, causal, softmax_scale, br, bc):
+    return _backward(q, k, v, o, do, lse, causal, softmax_scale)
+
+
+def forward(q, k, v, causal, softmax_scale, br, bc):
+    return _forward(q, k, v, causal, softmax_scale)
+
+
+def backward(q, k, v, o, do, lse, causal, softmax_scale, br, bc):
+    return _backward(q, k, v, o, do, lse, causal, softmax_scale)
+
+
+def _reject_fp8(fp8):
+    if fp8:
+        raise NotImplementedError(
+            "fp8=True: the reference's fp8 emulation is numerically broken (SURVEY.md D5) and has no pinned parity; "
+            "a real e4m3 tcgen05 path is a later row of the scope table"
+        )
+
+
+def fa3_forward(q, k, v, causal, softmax_scale, br, bc, stages, fp8):
+    _reject_fp8(fp8)
+    return _forward(q, k, v, causal, softmax_scale)
+
+
+def fa3_backward(q, k, v, o, do, lse, causal, softmax_scale, br, bc, stages, fp8):
+    _reject_fp8(fp8)
+    return _backward(q, k, v, o, do, lse, causal, softmax_scale)

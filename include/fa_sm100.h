@@ -1,0 +1,110 @@
+/*
+ * fa_sm100.h — C ABI of libfa_sm100.so: fused tiled attention forward + backward for NVIDIA B200 (sm_100a).
+ *
+ * This is the drop-in boundary for the reference's native extension.  The reference binds six functions on one
+ * pybind11 module (reference csrc/common/torch.extension.cpp:73-83):
+ *     fa1_forward / forward / fa3_forward      -> fa_sm100_fwd
+ *     fa1_backward / backward / fa3_backward   -> fa_sm100_bwd_delta + fa_sm100_bwd + fa_sm100_dq_finish
+ * FA1/FA2/FA3 are the same mathematical operator in the reference (csrc/fa1/fa1_fwd.cu:30-107,
+ * csrc/fa2/fa2_fwd.cu:30-106, csrc/fa3/fa3_fwd.cu:103-211), so one kernel family serves all three.
+ *
+ * Conventions
+ *   - plain C: pointers, sizes, a POD shape struct; no torch types, no exceptions, no allocation inside the library.
+ *   - all tensor pointers are DEVICE pointers, 16-byte aligned; rows are dense (row stride == d elements).
+ *     q/o/do/dq: (bh, n_q, d)   k/v/dk/dv: (bh, n_kv, d)   lse/delta: (bh, n_q) fp32.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream).  Calls only enqueue work.
+ *   - every function returns 0 on success or a negative FA_SM100_E* code; fa_sm100_strerror() names it.
+ *   - re-entrant and thread-safe: no global mutable state except a once-initialised driver entry point.
+ */
+#ifndef FA_SM100_H_
+#define FA_SM100_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FA_SM100_VERSION 100
+
+#define FA_SM100_DTYPE_F16 0
+#define FA_SM100_DTYPE_BF16 1
+
+#define FA_SM100_OK 0
+#define FA_SM100_EINVAL_DTYPE (-1)   /* dtype is not fp16 / bf16 */
+#define FA_SM100_EINVAL_HEADDIM (-2) /* d is not 64 or 128 (the host shim zero-pads other head dims) */
+#define FA_SM100_EINVAL_SHAPE (-3)   /* non-positive sizes, sizes beyond int32 tile indexing, bad strides */
+#define FA_SM100_EINVAL_PTR (-4)     /* NULL or mis-aligned tensor pointer */
+#define FA_SM100_EINVAL_SCALE (-5)   /* softmax_scale must be finite and > 0 */
+#define FA_SM100_EDRIVER (-6)        /* could not resolve / call cuTensorMapEncodeTiled */
+#define FA_SM100_ELAUNCH (-7)        /* kernel launch failed (cudaGetLastError) */
+#define FA_SM100_EDEVICE (-8)        /* current device is not compute capability 10.x */
+
+/* Problem geometry shared by all entry points. */
+typedef struct fa_sm100_shape {
+  int64_t bh;            /* number of independent (batch*head) slices                                  */
+  int64_t n_q;           /* query rows per slice                                                       */
+  int64_t n_kv;          /* key/value rows per slice                                                   */
+  int32_t d;             /* head dim: 64 or 128                                                        */
+  int32_t dtype;         /* FA_SM100_DTYPE_*                                                           */
+  int32_t causal;        /* 0/1; key c is visible to query r iff kv_col0 + c <= q_row0 + r             */
+  float softmax_scale;   /* S = Q K^T * softmax_scale                                                  */
+  int64_t q_row0;        /* global sequence index of query row 0 (ring attention; 0 otherwise)         */
+  int64_t kv_col0;       /* global sequence index of key row 0                                         */
+  int64_t q_bh_stride;   /* elements between slices of q / o / do / dq / dq_accum (0 => n_q * d)       */
+  int64_t kv_bh_stride;  /* elements between slices of k / v / dk / dv                (0 => n_kv * d)  */
+  int64_t lse_bh_stride; /* elements between slices of lse / delta                    (0 => n_q)       */
+} fa_sm100_shape;
+
+int fa_sm100_version(void);
+const char* fa_sm100_strerror(int code);
+
+/* Scratch the caller must provide to fa_sm100_bwd: an fp32 dQ accumulator of bh * n_q * d elements. */
+size_t fa_sm100_dq_accum_bytes(const fa_sm100_shape* s);
+
+/*
+ * Forward.  Replaces fa{1,2,3}_forward (reference csrc/fa1/fa1_fwd.cu:30-107):
+ *   O = softmax(Q K^T * scale [+ causal mask]) V      -> o   (q's dtype)
+ *   lse = rowmax + log(rowsum), natural log units     -> lse (fp32)
+ * Rows with no visible key produce O = 0, lse = -inf.
+ * Ring attention: if o_prev / lse_prev are non-NULL the new partial is merged with them by log-sum-exp
+ *   lse' = logaddexp(lse_prev, lse);  O' = e^{lse_prev-lse'} O_prev + e^{lse-lse'} O
+ * before write-out (o_prev may alias o, lse_prev may alias lse).
+ */
+int fa_sm100_fwd(const fa_sm100_shape* s, const void* q, const void* k, const void* v, void* o, float* lse,
+                 const void* o_prev, const float* lse_prev, void* stream);
+
+/* Backward pre-pass: delta[bh, r] = sum_c dO[bh, r, c] * O[bh, r, c]  (reference csrc/fa1/fa1_bwd.cu:57). */
+int fa_sm100_bwd_delta(const fa_sm100_shape* s, const void* o, const void* d_o, float* delta, void* stream);
+
+/*
+ * Backward main pass, KV-outer (reference csrc/fa1/fa1_bwd.cu:70-110 with the Python skip rule of
+ * src/fa1/torch/impl.py:89): recomputes P = exp(S - lse), then
+ *   dV = P^T dO,  dP = dO V^T,  dS = P o (dP - delta),  dK = scale * dS^T Q   -> dk, dv (input dtype)
+ *   dQ partials (unscaled) are reduce-added in fp32 into dq_accum, which the caller zeroes beforehand.
+ * If accumulate_dkv != 0, dk / dv are fp32 buffers of (bh, n_kv, d) and the results are ADDED to them
+ * (ring attention backward, where dK/dV travel with their K/V block); otherwise they are written in `dtype`.
+ */
+int fa_sm100_bwd(const fa_sm100_shape* s, const void* q, const void* k, const void* v, const void* d_o,
+                 const float* lse, const float* delta, float* dq_accum, void* dk, void* dv, int accumulate_dkv,
+                 void* stream);
+
+/* dq[i] = cast(dq_accum[i] * softmax_scale).  (The reference scales per tile: csrc/fa1/fa1_bwd.cu:102-103.) */
+int fa_sm100_dq_finish(const fa_sm100_shape* s, const float* dq_accum, void* dq, void* stream);
+
+/* out[i] = cast(acc[i] * alpha) for n contiguous elements: converts fp32 ring accumulators to `dtype`. */
+int fa_sm100_cast_scaled(const float* acc, void* out, int64_t n, float alpha, int32_t dtype, void* stream);
+
+/*
+ * Bring-up self-test for the hand-encoded UMMA/TMA descriptors: one 128x128x128 MMA through each operand path the
+ * attention kernels use.  mode 0: D = A B^T (A,B K-major smem)   1: D = A B (B MN-major smem)
+ *                         2: D = A B (A from TMEM, B MN-major)   3: D = A^T B (A,B MN-major smem)
+ * a, b: 128x128 row-major `dtype`; out: 128x128 fp32.  Not part of the reference surface.
+ */
+int fa_sm100_probe_umma(int mode, int32_t dtype, const void* a, const void* b, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FA_SM100_H_ */

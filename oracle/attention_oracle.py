@@ -1,0 +1,212 @@
+"""CPU oracle for the attention forward/backward hot path.  TEST INFRASTRUCTURE ONLY.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline / ``--impl reference`` legs may import
+this module; the product path (``flashattention-pytorch_b200/``) never does and has no CPU fallback.
+
+Parity status: PINNED.  ``tests/test_oracle_golden.py`` checks every function here against
+  * outputs of the reference's own Python implementation (``fa1_forward_torch`` / ``fa1_backward_torch`` /
+    ``fa3_forward_torch`` / non-causal ``reference_attention`` + autograd) generated in the build container by
+    ``oracle/make_golden.py`` and committed under ``tests/golden/``;
+  * and, when present, the reference's csrc compiled for CPU (``oracle/_ref``, built by ``oracle/build_ref.py``).
+The reference holds no golden vectors of its own: its tests compute expectations on the fly.
+
+Two restatements of the same operator, fp32 arithmetic on whatever dtype the inputs have (inputs are up-cast, as the
+reference does):
+
+``dense_forward`` / ``dense_backward``
+    follows reference ``src/common/correctness.py:5-34``: ``softmax(Q K^T * scale [+ causal]) V``, ``o.to(q.dtype)``,
+    ``lse = logsumexp``; gradients by autograd through the fp32 graph, returned in the input dtype.  The causal mask
+    is the rule of reference ``src/fa1/torch/impl.py:18-24`` (key ``c`` hidden from query ``r`` iff ``c > r``) applied
+    to the last two dims — the reference's own ``reference_attention(causal=True)`` applies it to the wrong axes
+    (SURVEY.md defect D1), so that one call site is intentionally NOT followed.
+
+``blocked_forward`` / ``blocked_backward``
+    follows reference ``src/fa1/torch/impl.py:26-68`` and ``:70-115``: the tiled online-softmax recurrence and the
+    KV-outer backward with ``P = exp(S - lse)``; vectorised over the batch*head dimension so it is usable at a few
+    thousand rows.  Supports the ring-attention generalisation (``q_row0`` / ``kv_col0`` offsets, n_q != n_kv).
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+
+NEG_INF = float("-inf")
+
+
+def _as_bh(x):
+    """(B,H,N,D) or (BH,N,D) -> (BH,N,D), plus the (B,H) to restore (reference src/common/utils.py:3-7)."""
+    if x.dim() == 4:
+        return x.reshape(x.shape[0] * x.shape[1], x.shape[2], x.shape[3]), (x.shape[0], x.shape[1])
+    return x, None
+
+
+def visible_mask(n_q, n_kv, q_row0=0, kv_col0=0, device="cpu"):
+    """True where key c is visible to query r under the causal rule  kv_col0 + c <= q_row0 + r
+    (reference src/fa1/torch/impl.py:18-24 with both offsets zero)."""
+    r = torch.arange(n_q, device=device)[:, None] + q_row0
+    c = torch.arange(n_kv, device=device)[None, :] + kv_col0
+    return c <= r
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# dense
+# ----------------------------------------------------------------------------------------------------------------------
+def dense_forward(q, k, v, causal=False, softmax_scale=None, q_row0=0, kv_col0=0):
+    """reference src/common/correctness.py:5-24.  Returns (o in q.dtype, lse fp32)."""
+    if softmax_scale is None:
+        softmax_scale = q.shape[-1] ** -0.5
+    qb, bh_shape = _as_bh(q)
+    kb, _ = _as_bh(k)
+    vb, _ = _as_bh(v)
+    s = torch.matmul(qb.float(), kb.float().transpose(-2, -1)) * softmax_scale
+    if causal:
+        s = s.masked_fill(~visible_mask(qb.shape[1], kb.shape[1], q_row0, kv_col0, s.device), NEG_INF)
+    lse = torch.logsumexp(s, dim=-1)
+    p = torch.exp(s - torch.where(torch.isinf(lse), torch.zeros_like(lse), lse)[..., None])  # all-masked row -> 0
+    o = torch.matmul(p, vb.float()).to(q.dtype)
+    if bh_shape is not None:
+        o = o.reshape(*bh_shape, *o.shape[1:])
+        lse = lse.reshape(*bh_shape, lse.shape[-1])
+    return o, lse
+
+
+def dense_backward(q, k, v, do, causal=False, softmax_scale=None, q_row0=0, kv_col0=0):
+    """reference src/common/correctness.py:26-34: autograd through the dense fp32 graph.
+    Returns (dq, dk, dv, o, lse); grads in the input dtype."""
+    qr = q.detach().clone().requires_grad_(True)
+    kr = k.detach().clone().requires_grad_(True)
+    vr = v.detach().clone().requires_grad_(True)
+    o, lse = dense_forward(qr, kr, vr, causal, softmax_scale, q_row0, kv_col0)
+    o.backward(do.to(o.dtype))
+    return qr.grad, kr.grad, vr.grad, o.detach(), lse.detach()
+
+
+def dense_backward_fp32(q, k, v, do, causal=False, softmax_scale=None, q_row0=0, kv_col0=0):
+    """Closed-form fp32 gradients (no rounding of O or the grads to the input dtype): the target a 16-bit kernel
+    with fp32 accumulation should be compared with.  Same maths as reference csrc/fa1/fa1_bwd.cu:57,96-104."""
+    if softmax_scale is None:
+        softmax_scale = q.shape[-1] ** -0.5
+    qb, bh_shape = _as_bh(q)
+    kb, _ = _as_bh(k)
+    vb, _ = _as_bh(v)
+    dob, _ = _as_bh(do)
+    qf, kf, vf, dof = qb.float(), kb.float(), vb.float(), dob.float()
+    s = torch.matmul(qf, kf.transpose(-2, -1)) * softmax_scale
+    if causal:
+        s = s.masked_fill(~visible_mask(qf.shape[1], kf.shape[1], q_row0, kv_col0, s.device), NEG_INF)
+    lse = torch.logsumexp(s, dim=-1)
+    p = torch.exp(s - torch.where(torch.isinf(lse), torch.zeros_like(lse), lse)[..., None])
+    o = torch.matmul(p, vf)
+    delta = (dof * o).sum(-1, keepdim=True)
+    dv = torch.matmul(p.transpose(-2, -1), dof)
+    dp = torch.matmul(dof, vf.transpose(-2, -1))
+    ds = p * (dp - delta)
+    dq = torch.matmul(ds, kf) * softmax_scale
+    dk = torch.matmul(ds.transpose(-2, -1), qf) * softmax_scale
+    outs = [dq, dk, dv, o, lse]
+    if bh_shape is not None:
+        outs = [t.reshape(*bh_shape, *t.shape[1:]) for t in outs]
+    return tuple(outs)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# blocked (tiled) — the algorithm the kernels implement
+# ----------------------------------------------------------------------------------------------------------------------
+def blocked_forward(q, k, v, causal, softmax_scale, br=128, bc=128, q_row0=0, kv_col0=0):
+    """reference src/fa1/torch/impl.py:26-68 on (BH,N,D) tensors, all slices at once.
+    Tile skip: a KV tile is skipped iff its first key is hidden from the tile's last query (``:15-16,41-42``);
+    the element mask is applied wherever a tile straddles the diagonal."""
+    bh, n_q, d = q.shape
+    n_kv = k.shape[1]
+    o = torch.empty((bh, n_q, d), dtype=q.dtype, device=q.device)
+    lse = torch.empty((bh, n_q), dtype=torch.float32, device=q.device)
+    for r0 in range(0, n_q, br):
+        r1 = min(r0 + br, n_q)
+        qi = q[:, r0:r1].float()
+        m = torch.full((bh, r1 - r0), NEG_INF)
+        l = torch.zeros((bh, r1 - r0))
+        acc = torch.zeros((bh, r1 - r0, d))
+        for c0 in range(0, n_kv, bc):
+            if causal and kv_col0 + c0 > q_row0 + r1 - 1:
+                break
+            c1 = min(c0 + bc, n_kv)
+            s = torch.matmul(qi, k[:, c0:c1].float().transpose(-2, -1)) * softmax_scale
+            if causal and kv_col0 + c1 - 1 > q_row0 + r0:
+                rr = torch.arange(r0, r1)[:, None] + q_row0
+                cc = torch.arange(c0, c1)[None, :] + kv_col0
+                s = s.masked_fill(cc > rr, NEG_INF)
+            m_new = torch.maximum(m, s.amax(dim=-1))
+            m_safe = torch.where(torch.isinf(m_new), torch.zeros_like(m_new), m_new)
+            p = torch.exp(s - m_safe[..., None])
+            alpha = torch.exp(m - m_safe)
+            l = alpha * l + p.sum(-1)
+            acc = alpha[..., None] * acc + torch.matmul(p, v[:, c0:c1].float())
+            m = m_new
+        safe_l = torch.where(l > 0, l, torch.ones_like(l))
+        o[:, r0:r1] = (acc / safe_l[..., None]).to(q.dtype)
+        lse[:, r0:r1] = torch.where(l > 0, m + torch.log(safe_l), torch.full_like(l, NEG_INF))
+    return o, lse
+
+
+def blocked_backward(q, k, v, o, do, lse, causal, softmax_scale, br=128, bc=128, q_row0=0, kv_col0=0,
+                     out_dtype=None):
+    """reference src/fa1/torch/impl.py:70-115: KV-outer / Q-inner, P recomputed from the saved lse.
+    Returns (dq, dk, dv) in ``out_dtype`` (default: input dtype, like the reference's ``.to(q.dtype)``)."""
+    bh, n_q, d = q.shape
+    n_kv = k.shape[1]
+    dq = torch.zeros((bh, n_q, d))
+    dk = torch.zeros((bh, n_kv, d))
+    dv = torch.zeros((bh, n_kv, d))
+    delta = (do.float() * o.float()).sum(-1)
+    lse_safe = torch.where(torch.isinf(lse), torch.zeros_like(lse), lse).float()
+    for c0 in range(0, n_kv, bc):
+        c1 = min(c0 + bc, n_kv)
+        kj, vj = k[:, c0:c1].float(), v[:, c0:c1].float()
+        for r0 in range(0, n_q, br):
+            r1 = min(r0 + br, n_q)
+            if causal and kv_col0 + c0 > q_row0 + r1 - 1:
+                continue
+            qi, doi = q[:, r0:r1].float(), do[:, r0:r1].float()
+            s = torch.matmul(qi, kj.transpose(-2, -1)) * softmax_scale
+            if causal and kv_col0 + c1 - 1 > q_row0 + r0:
+                rr = torch.arange(r0, r1)[:, None] + q_row0
+                cc = torch.arange(c0, c1)[None, :] + kv_col0
+                s = s.masked_fill(cc > rr, NEG_INF)
+            p = torch.exp(s - lse_safe[:, r0:r1, None])
+            dv[:, c0:c1] += torch.matmul(p.transpose(-2, -1), doi)
+            dp = torch.matmul(doi, vj.transpose(-2, -1))
+            ds = p * (dp - delta[:, r0:r1, None])
+            dq[:, r0:r1] += torch.matmul(ds, kj) * softmax_scale
+            dk[:, c0:c1] += torch.matmul(ds.transpose(-2, -1), qi) * softmax_scale
+    out_dtype = out_dtype or q.dtype
+    return dq.to(out_dtype), dk.to(out_dtype), dv.to(out_dtype)
+
+
+def merge_partials(o_a, lse_a, o_b, lse_b):
+    """Log-sum-exp merge of two attention partials over disjoint key sets (the ring-attention combine; derived from
+    the online-softmax update of reference src/fa1/torch/impl.py:53-62)."""
+    lse = torch.logaddexp(lse_a, lse_b)
+    safe = torch.where(torch.isinf(lse), torch.zeros_like(lse), lse)
+    wa = torch.exp(lse_a - safe)[..., None]
+    wb = torch.exp(lse_b - safe)[..., None]
+    return (wa * o_a.float() + wb * o_b.float()), lse
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# error report (SURVEY.md §8d "Parity report")
+# ----------------------------------------------------------------------------------------------------------------------
+def error_report(actual, expected, rtol, atol):
+    a, e = actual.detach().float().cpu(), expected.detach().float().cpu()
+    finite = torch.isfinite(e)
+    same_inf = (~finite) & (a == e)
+    diff = torch.where(finite, (a - e).abs(), torch.where(same_inf, torch.zeros_like(a), torch.full_like(a, math.inf)))
+    big = finite & (e.abs() > 1e-2)
+    rel = torch.where(big, diff / e.abs().clamp_min(1e-30), torch.zeros_like(diff))
+    viol = diff > (atol + rtol * torch.where(finite, e.abs(), torch.zeros_like(e)))
+    return {
+        "max_abs": float(diff.max()) if diff.numel() else 0.0,
+        "max_rel": float(rel.max()) if rel.numel() else 0.0,
+        "violations": int(viol.sum()),
+        "numel": int(diff.numel()),
+    }

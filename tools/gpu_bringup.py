@@ -1,0 +1,83 @@
+"""GPU bring-up script (run under gpurun): UMMA descriptor probe, then forward parity on a ladder of shapes.
+Each stage runs in its own subprocess so a faulting kernel does not take the rest down."""
+import subprocess
+import sys
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path[:0] = [str(ROOT / "flashattention-pytorch_b200"), str(ROOT)]
+
+
+def stage_probe(mode, dtype_name):
+    import torch
+    import flashattention_lab_cuda as ext
+
+    dt = getattr(torch, dtype_name)
+    torch.manual_seed(mode)
+    a = torch.randn(128, 128, device="cuda", dtype=dt)
+    b = torch.randn(128, 128, device="cuda", dtype=dt)
+    out = ext.probe_umma(mode, a, b)
+    torch.cuda.synchronize()
+    af, bf = a.float(), b.float()
+    want = {0: af @ bf.T, 1: af @ bf, 2: af @ bf, 3: af.T @ bf}[mode]
+    err = (out - want).abs().max().item()
+    print(f"probe mode={mode} {dtype_name}: max_abs_err={err:.4e} ref_max={want.abs().max().item():.2f}", flush=True)
+    if err > 1e-2:
+        # help diagnose layout mistakes: compare against a few plausible alternatives
+        alts = {"A@B.T": af @ bf.T, "A@B": af @ bf, "A.T@B": af.T @ bf, "A.T@B.T": af.T @ bf.T}
+        for name, alt in alts.items():
+            print(f"    vs {name}: {(out - alt).abs().max().item():.4e}")
+        print("    out[0,:8]", out[0, :8].tolist())
+        print("    want[0,:8]", want[0, :8].tolist())
+        return 1
+    return 0
+
+
+def stage_fwd(bh, n, d, dtype_name, causal):
+    import torch
+    import flashattention_lab_cuda as ext
+    from oracle.attention_oracle import dense_forward, error_report
+
+    dt = getattr(torch, dtype_name)
+    torch.manual_seed(1234)
+    q, k, v = (torch.randn(bh, n, d, device="cuda", dtype=dt) for _ in range(3))
+    o, lse = ext.fwd_raw(q, k, v, causal, d ** -0.5)
+    torch.cuda.synchronize()
+    o_ref, lse_ref = dense_forward(q.cpu(), k.cpu(), v.cpu(), causal, d ** -0.5)
+    ro = error_report(o, o_ref, 5e-2, 5e-2)
+    rl = error_report(lse, lse_ref, 1e-3, 1e-3)
+    ok = ro["violations"] == 0 and rl["violations"] == 0
+    print(f"fwd bh={bh} n={n} d={d} {dtype_name} causal={causal}: O max_abs={ro['max_abs']:.3e} viol={ro['violations']} "
+          f"| LSE max_abs={rl['max_abs']:.3e} viol={rl['violations']} -> {'OK' if ok else 'FAIL'}", flush=True)
+    return 0 if ok else 1
+
+
+def main():
+    if len(sys.argv) > 1:
+        kind = sys.argv[1]
+        if kind == "probe":
+            sys.exit(stage_probe(int(sys.argv[2]), sys.argv[3]))
+        if kind == "fwd":
+            sys.exit(stage_fwd(int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]), sys.argv[5], sys.argv[6] == "1"))
+    stages = [["probe", str(m), dt] for m in range(4) for dt in ("bfloat16", "float16")]
+    for bh, n, d, dt in [(1, 128, 128, "bfloat16"), (2, 256, 128, "bfloat16"), (2, 33, 64, "float16"),
+                         (3, 300, 64, "float16"), (2, 1024, 128, "bfloat16"), (2, 777, 128, "float16"),
+                         (4, 2048, 64, "bfloat16")]:
+        for causal in ("0", "1"):
+            stages.append(["fwd", str(bh), str(n), str(d), dt, causal])
+    fails = 0
+    for st in stages:
+        try:
+            r = subprocess.run([sys.executable, __file__, *st], timeout=180)
+            rc = r.returncode
+        except subprocess.TimeoutExpired:
+            rc = -999
+        if rc != 0:
+            fails += 1
+            print(f"STAGE {' '.join(st)} -> rc={rc}", flush=True)
+    print(f"bring-up done: {fails} failing stages of {len(stages)}")
+    sys.exit(0)
+
+
+if __name__ == "__main__":
+    main()
