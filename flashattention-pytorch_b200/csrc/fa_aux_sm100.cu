@@ -1,50 +1,9 @@
-// HBM-bound helper kernels of the backward (delta pre-pass, dQ finish, fp32 -> 16-bit cast), library metadata, and
+// HBM-bound helper kernels of the backward (dQ finish, fp32 -> 16-bit cast), library metadata, and
 // the UMMA/TMA descriptor bring-up probe.
 #include "ptx.cuh"
 #include "fa_host.cuh"
 
 namespace fa {
-
-// ------------------------------------------------------------------------------------------------
-// delta[bh, r] = sum_c dO[bh, r, c] * O[bh, r, c]     (reference csrc/fa1/fa1_bwd.cu:57)
-// One warp per row; D/8 lanes each load one 16-byte vector of O and dO.  Algorithmic bytes: 2 * D * 2 + 4 per row.
-// ------------------------------------------------------------------------------------------------
-template <int D, bool kBF16>
-__global__ void __launch_bounds__(256) fa_bwd_delta_kernel(const uint16_t* __restrict__ o,
-                                                           const uint16_t* __restrict__ d_o, float* __restrict__ delta,
-                                                           long long n_q, long long bh, long long q_bh_stride,
-                                                           long long lse_bh_stride) {
-  constexpr int kLanesPerRow = D / 8;            // 16 (D=128) or 8 (D=64) lanes x 8 elements
-  constexpr int kRowsPerWarp = 32 / kLanesPerRow;
-  const int lane = threadIdx.x & 31;
-  const int sub = lane / kLanesPerRow, li = lane % kLanesPerRow;
-  const long long warp_global = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-  const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
-  const long long total_rows = bh * n_q;
-  for (long long r0 = warp_global * kRowsPerWarp; r0 < total_rows; r0 += nwarps * kRowsPerWarp) {
-    const long long r = r0 + sub;
-    float acc = 0.f;
-    if (r < total_rows) {
-      const long long b = r / n_q, rr = r % n_q;
-      const long long off = b * q_bh_stride + rr * D + li * 8;
-      const uint4 a = *reinterpret_cast<const uint4*>(o + off);
-      const uint4 g = *reinterpret_cast<const uint4*>(d_o + off);
-      const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, gw[4] = {g.x, g.y, g.z, g.w};
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float2 x = unpack2<kBF16>(aw[i]), y = unpack2<kBF16>(gw[i]);
-        acc = fmaf(x.x, y.x, acc);
-        acc = fmaf(x.y, y.y, acc);
-      }
-    }
-#pragma unroll
-    for (int s = kLanesPerRow / 2; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
-    if (r < total_rows && li == 0) {
-      const long long b = r / n_q, rr = r % n_q;
-      delta[b * lse_bh_stride + rr] = acc;
-    }
-  }
-}
 
 // out = cast(acc * alpha), 8 elements per thread (two 16-byte loads, one 16-byte store)
 template <bool kBF16>
@@ -221,29 +180,6 @@ extern "C" const char* fa_sm100_strerror(int code) {
 extern "C" size_t fa_sm100_dq_accum_bytes(const fa_sm100_shape* s) {
   if (!s || s->bh <= 0 || s->n_q <= 0 || s->d <= 0) return 0;
   return static_cast<size_t>(s->bh) * static_cast<size_t>(s->n_q) * static_cast<size_t>(s->d) * sizeof(float);
-}
-
-extern "C" int fa_sm100_bwd_delta(const fa_sm100_shape* s, const void* o, const void* d_o, float* delta,
-                                  void* stream) {
-  fa::Geometry g;
-  int rc = fa::check_shape(s, &g);
-  if (rc) return rc;
-  if (!fa::aligned16(o) || !fa::aligned16(d_o) || delta == nullptr) return FA_SM100_EINVAL_PTR;
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const long long rows = g.bh * g.n_q;
-  const int rows_per_block = (256 / 32) * (32 / (g.d / 8));
-  const int grid = fa::grid_for(rows, rows_per_block);
-  const uint16_t* op = static_cast<const uint16_t*>(o);
-  const uint16_t* gp = static_cast<const uint16_t*>(d_o);
-  const bool bf = g.dtype == FA_SM100_DTYPE_BF16;
-  if (g.d == 128) {
-    if (bf) fa::fa_bwd_delta_kernel<128, true><<<grid, 256, 0, st>>>(op, gp, delta, g.n_q, g.bh, g.q_bh_stride, g.lse_bh_stride);
-    else fa::fa_bwd_delta_kernel<128, false><<<grid, 256, 0, st>>>(op, gp, delta, g.n_q, g.bh, g.q_bh_stride, g.lse_bh_stride);
-  } else {
-    if (bf) fa::fa_bwd_delta_kernel<64, true><<<grid, 256, 0, st>>>(op, gp, delta, g.n_q, g.bh, g.q_bh_stride, g.lse_bh_stride);
-    else fa::fa_bwd_delta_kernel<64, false><<<grid, 256, 0, st>>>(op, gp, delta, g.n_q, g.bh, g.q_bh_stride, g.lse_bh_stride);
-  }
-  return fa::launch_status();
 }
 
 extern "C" int fa_sm100_dq_finish(const fa_sm100_shape* s, const float* dq_accum, void* dq, void* stream) {

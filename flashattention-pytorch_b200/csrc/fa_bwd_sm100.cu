@@ -1,6 +1,525 @@
-// placeholder until the KV-outer backward kernel lands
+// Fused attention backward for sm_100a, KV-outer: one CTA owns a 128-row K/V tile, streams the visible 128-row
+// Q / dO tiles past it, keeps dK and dV accumulators in TMEM, and reduce-adds its dQ partials into an fp32 buffer.
+//
+// Replaces the reference's host-side ATen loops fa{1,2,3}_backward (csrc/fa1/fa1_bwd.cu:70-110; algorithmic twin
+// src/fa1/torch/impl.py:70-115, whose causal block rule `skip iff first key > last query` is the one used here):
+//   S = Q K^T * scale,  P = exp(S - lse),  dV += P^T dO,  dP = dO V^T,  dS = P o (dP - delta),
+//   dQ += dS K * scale,  dK += dS^T Q * scale.
+// Everything is computed TRANSPOSED (kv rows on TMEM lanes) so that P^T and dS^T are already in the layout the
+// tensor core wants for an A operand read straight from TMEM:
+//   S^T  = K  Q^T      (A = K  smem K-major,  B = Q  smem K-major)            -> TMEM ST
+//   dP^T = V  dO^T     (A = V  smem K-major,  B = dO smem K-major)            -> TMEM DPT
+//   dV  += P^T  dO     (A = P^T  in TMEM,     B = dO smem MN-major)           -> TMEM DV
+//   dK  += dS^T Q      (A = dS^T in TMEM,     B = Q  smem MN-major)           -> TMEM DK
+//   dQ   = dS   K      (A = dS^T smem read MN-major, B = K smem MN-major)     -> TMEM DPT (aliases dP^T/dS^T)
+// TMEM columns: ST [0,128)  DPT [128,256)  DV [256,256+D)  DK [256+D,256+2D).
+//
+// Warps: 0-3 / 4-7 compute warpgroups (thread = kv row; WG0 takes query columns 0-63, WG1 64-127),
+//        8-11 dQ drain warpgroup (TMEM -> swizzled smem -> TMA reduce-add, thread = query row),
+//        12 TMA producer, 13 MMA issuer.
+#include "ptx.cuh"
 #include "fa_host.cuh"
-extern "C" int fa_sm100_bwd(const fa_sm100_shape*, const void*, const void*, const void*, const void*, const float*,
-                            const float*, float*, void*, void*, int, void*) {
-  return FA_SM100_ELAUNCH;
+
+namespace fa {
+
+struct BwdParams {
+  const float* rowstats;  // (bh, nqt, 2, 128): lse*log2e then delta, per 128-row query tile
+  int n_q, n_kv, bh, causal, diag, nqt, nkt;
+  float scale_log2, scale;
+};
+
+constexpr int kBwdThreads = 448;
+constexpr int kT = 128;  // tile edge (query rows and kv rows)
+
+template <int D>
+struct BwdCfg {
+  static constexpr int kTileBytes = kT * D * 2;  // Q / K / V / dO tile
+  static constexpr int kSub = kT * 128;          // one 64-column swizzled sub-tile (128 rows x 128 B)
+  static constexpr int kDsBytes = kT * kT * 2;   // dS^T tile (kv x q), 16-bit
+  static constexpr int kDqStageBytes = kT * 32 * 4;  // 128 rows x 32 fp32 columns
+  static constexpr int kOffK = 0;
+  static constexpr int kOffV = kOffK + kTileBytes;
+  static constexpr int kOffQ = kOffV + kTileBytes;       // 2 stages
+  static constexpr int kOffDO = kOffQ + 2 * kTileBytes;  // 1 stage
+  static constexpr int kOffDS = kOffDO + kTileBytes;
+  static constexpr int kOffDQ = kOffDS + kDsBytes;        // 2 staging buffers
+  static constexpr int kOffStats = kOffDQ + 2 * kDqStageBytes;  // 2 stages x 1 KiB
+  static constexpr int kOffBars = kOffStats + 2 * 1024;
+  static constexpr int kSmemBytes = kOffBars + 256;
+};
+static_assert(BwdCfg<128>::kSmemBytes <= 232448, "backward smem budget");
+
+enum BwdBar : int {
+  kBarKV = 0, kBarQFull0, kBarQFull1, kBarQEmpty0, kBarQEmpty1, kBarDOFull, kBarDOEmpty, kBarSFull, kBarDPFull,
+  kBarPReady, kBarDSReady, kBarDQFull, kBarDQDrained, kBarDKVDone, kBarCount
+};
+
+template <int D, bool kBF16>
+__global__ void __launch_bounds__(kBwdThreads, 1)
+fa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
+              const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_do,
+              const __grid_constant__ CUtensorMap tm_dq, const __grid_constant__ CUtensorMap tm_dk,
+              const __grid_constant__ CUtensorMap tm_dv, const BwdParams p) {
+  using Cfg = BwdCfg<D>;
+  constexpr int kSub = Cfg::kSub;
+  constexpr int kChunks = D / 64;
+
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* k_smem = smem + Cfg::kOffK;
+  uint8_t* v_smem = smem + Cfg::kOffV;
+  uint8_t* q_smem = smem + Cfg::kOffQ;
+  uint8_t* do_smem = smem + Cfg::kOffDO;
+  uint8_t* ds_smem = smem + Cfg::kOffDS;
+  uint8_t* dq_smem = smem + Cfg::kOffDQ;
+  float* stats_smem = reinterpret_cast<float*>(smem + Cfg::kOffStats);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kOffBars);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kBarCount);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int bh = blockIdx.x / p.nkt;
+  const int j = blockIdx.x % p.nkt;  // kv tile; ascending = heaviest first under the causal mask
+  int i_min = 0;
+  if (p.causal) {
+    const int first = j * kT - p.diag;  // first query row that sees this tile's first key
+    i_min = first > 0 ? first / kT : 0;
+  }
+  const int n_iter = p.nqt > i_min ? p.nqt - i_min : 0;
+
+  if (threadIdx.x == 0) {
+    if (smem_u32(smem) & 1023u) {
+      printf("fa_sm100 bwd: dynamic smem base not 1024-aligned\n");
+      __trap();
+    }
+    for (int b = 0; b < kBarCount; ++b) {
+      const uint32_t count = (b == kBarPReady || b == kBarDSReady) ? 256u : (b == kBarDQDrained ? 128u : 1u);
+      mbar_init(&bars[b], count);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 12 && lane == 0) {
+    tma_prefetch_desc(&tm_q);
+    tma_prefetch_desc(&tm_k);
+    tma_prefetch_desc(&tm_v);
+    tma_prefetch_desc(&tm_do);
+    tma_prefetch_desc(&tm_dq);
+  }
+  if (warp == 13) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  constexpr uint32_t kColST = 0, kColDPT = 128, kColDV = 256, kColDK = 256 + D;
+
+  if (warp == 12) {
+    // ===================================== TMA producer =====================================
+    if (lane == 0) {
+      mbar_arrive_expect_tx(&bars[kBarKV], 2 * Cfg::kTileBytes);
+      for (int c = 0; c < kChunks; ++c) {
+        tma_load_3d(k_smem + c * kSub, &tm_k, &bars[kBarKV], c * 64, j * kT, bh);
+        tma_load_3d(v_smem + c * kSub, &tm_v, &bars[kBarKV], c * 64, j * kT, bh);
+      }
+      for (int it = 0; it < n_iter; ++it) {
+        const int i = i_min + it, st = it & 1;
+        mbar_wait(&bars[kBarQEmpty0 + st], ((it >> 1) & 1) ^ 1);
+        mbar_arrive_expect_tx(&bars[kBarQFull0 + st], Cfg::kTileBytes + 1024);
+        for (int c = 0; c < kChunks; ++c)
+          tma_load_3d(q_smem + st * Cfg::kTileBytes + c * kSub, &tm_q, &bars[kBarQFull0 + st], c * 64, i * kT, bh);
+        bulk_load_1d(stats_smem + st * 256, p.rowstats + (static_cast<long long>(bh) * p.nqt + i) * 256, 1024,
+                     &bars[kBarQFull0 + st]);
+        mbar_wait(&bars[kBarDOEmpty], (it & 1) ^ 1);
+        mbar_arrive_expect_tx(&bars[kBarDOFull], Cfg::kTileBytes);
+        for (int c = 0; c < kChunks; ++c)
+          tma_load_3d(do_smem + c * kSub, &tm_do, &bars[kBarDOFull], c * 64, i * kT, bh);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 13) {
+    // ===================================== MMA issuer =====================================
+    if (lane == 0 && n_iter > 0) {
+      constexpr uint32_t idesc_s = umma_idesc(kBF16, kT, kT, false, false);
+      constexpr uint32_t idesc_acc = umma_idesc(kBF16, kT, D, false, true);
+      constexpr uint32_t idesc_dq = umma_idesc(kBF16, kT, D, true, true);
+      const uint32_t k_addr = smem_u32(k_smem), v_addr = smem_u32(v_smem), q_addr = smem_u32(q_smem),
+                     do_addr = smem_u32(do_smem), ds_addr = smem_u32(ds_smem);
+
+      // D[kv, q] = A[kv, :] . B[q, :]   (both K-major, contraction over the head dim)
+      auto mma_kmajor = [&](uint32_t d_col, uint32_t a_base, uint32_t b_base) {
+#pragma unroll
+        for (int kk = 0; kk < D / 16; ++kk) {
+          const uint32_t off = (kk >> 2) * kSub + (kk & 3) * 32;
+          umma_ss(tmem_base + d_col, umma_smem_desc(a_base + off, 16, 1024), umma_smem_desc(b_base + off, 16, 1024),
+                  idesc_s, kk > 0 ? 1u : 0u);
+        }
+      };
+      // D[kv, d] (+)= A^T-in-TMEM[kv, q] . B[q, d]   (contraction over the 128 query rows; B MN-major)
+      // the 16-bit A operand sits in columns [0,32) (queries 0-63, written by WG0) and [64,96) (queries 64-127, WG1)
+      auto mma_from_tmem = [&](uint32_t d_col, uint32_t a_col, uint32_t b_base, bool acc) {
+#pragma unroll
+        for (int kk = 0; kk < kT / 16; ++kk) {
+          const uint32_t a = tmem_base + a_col + (kk < 4 ? kk * 8 : 64 + (kk - 4) * 8);
+          umma_ts(tmem_base + d_col, a, umma_smem_desc(b_base + kk * 16 * 128, kSub, 1024), idesc_acc,
+                  (acc || kk > 0) ? 1u : 0u);
+        }
+      };
+      // dQ[q, d] = dS[q, kv] . K[kv, d]   (contraction over the 128 kv rows; both operands MN-major)
+      auto mma_dq = [&]() {
+#pragma unroll
+        for (int kk = 0; kk < kT / 16; ++kk) {
+          umma_ss(tmem_base + kColDPT, umma_smem_desc(ds_addr + kk * 16 * 128, kT * 128, 1024),
+                  umma_smem_desc(k_addr + kk * 16 * 128, kSub, 1024), idesc_dq, kk > 0 ? 1u : 0u);
+        }
+      };
+
+      mbar_wait(&bars[kBarKV], 0);
+      mbar_wait(&bars[kBarQFull0], 0);
+      tc_fence_after();
+      mma_kmajor(kColST, k_addr, q_addr);
+      tc_commit(&bars[kBarSFull]);
+      mbar_wait(&bars[kBarDOFull], 0);
+      tc_fence_after();
+      mma_kmajor(kColDPT, v_addr, do_addr);
+      tc_commit(&bars[kBarDPFull]);
+
+      for (int it = 0; it < n_iter; ++it) {
+        const int st = it & 1;
+        mbar_wait(&bars[kBarPReady], it & 1);
+        tc_fence_after();
+        mma_from_tmem(kColDV, kColST, do_addr, it > 0);
+        tc_commit(&bars[kBarDOEmpty]);
+
+        mbar_wait(&bars[kBarDSReady], it & 1);
+        tc_fence_after();
+        mma_from_tmem(kColDK, kColDPT, q_addr + st * Cfg::kTileBytes, it > 0);
+        tc_commit(&bars[kBarQEmpty0 + st]);
+        mma_dq();
+        tc_commit(&bars[kBarDQFull]);
+
+        if (it + 1 < n_iter) {
+          const int nst = st ^ 1;
+          mbar_wait(&bars[kBarQFull0 + nst], ((it + 1) >> 1) & 1);
+          tc_fence_after();
+          mma_kmajor(kColST, k_addr, q_addr + nst * Cfg::kTileBytes);
+          tc_commit(&bars[kBarSFull]);
+          mbar_wait(&bars[kBarDOFull], (it + 1) & 1);
+          mbar_wait(&bars[kBarDQDrained], it & 1);
+          tc_fence_after();
+          mma_kmajor(kColDPT, v_addr, do_addr);
+          tc_commit(&bars[kBarDPFull]);
+        }
+      }
+      tc_commit(&bars[kBarDKVDone]);
+    }
+    __syncwarp();
+  } else if (warp >= 8) {
+    // ===================================== dQ drain warpgroup =====================================
+    const int row = threadIdx.x - 256;  // query row inside the tile == TMEM lane
+    const uint32_t lane_sel = static_cast<uint32_t>((warp & 3) * 32) << 16;
+    for (int it = 0; it < n_iter; ++it) {
+      const int i = i_min + it;
+      mbar_wait(&bars[kBarDQFull], it & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int ch = 0; ch < D / 32; ++ch) {
+        uint8_t* buf = dq_smem + (ch & 1) * Cfg::kDqStageBytes;
+        if (row == 0) tma_store_wait_read<1>();  // the reduce that last used this buffer has read it
+        named_bar_sync(3, 128);
+        float v[32];
+        tmem_ld32(tmem_base + lane_sel + kColDPT + ch * 32, reinterpret_cast<uint32_t*>(v));
+        tc_wait_ld();
+        if (ch == D / 32 - 1) {
+          tc_fence_before();
+          mbar_arrive(&bars[kBarDQDrained]);
+        }
+        uint8_t* rowp = buf + row * 128;
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          *reinterpret_cast<float4*>(rowp + ((c ^ (row & 7)) << 4)) =
+              make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+        fence_proxy_async_smem();
+        named_bar_sync(3, 128);
+        if (row == 0) {
+          tma_reduce_add_3d(&tm_dq, buf, ch * 32, i * kT, bh);
+          tma_store_commit();
+        }
+      }
+    }
+    if (row == 0) tma_store_wait_all<0>();
+  } else {
+    // ===================================== compute warpgroups =====================================
+    const int wg = warp >> 2;
+    const int r = threadIdx.x & 127;  // kv row inside the tile == TMEM lane
+    const uint32_t lane_sel = static_cast<uint32_t>((warp & 3) * 32) << 16;
+    const int col_base = wg * 64;
+    const uint32_t t_st = tmem_base + lane_sel + kColST + col_base;
+    const uint32_t t_dpt = tmem_base + lane_sel + kColDPT + col_base;
+    uint8_t* ds_row = ds_smem + wg * (kT * 128) + r * 128;
+
+    for (int it = 0; it < n_iter; ++it) {
+      const int i = i_min + it, st = it & 1;
+      const float* ls = stats_smem + st * 256 + col_base;  // lse * log2e for this WG's 64 query columns
+      const float* dl = ls + 128;                          // delta
+      // key (j*128 + r) is visible to query (i*128 + c) iff c >= c_min
+      // ... and keys past n_kv (zero-filled by TMA) are never visible
+      const bool kv_tail = (j * kT + kT > p.n_kv);
+      int c_min = p.causal ? r + (j - i) * kT - p.diag : 0;
+      if (j * kT + r >= p.n_kv) c_min = 1 << 30;
+      const bool need_mask = kv_tail || (p.causal && (kT - 1 + (j - i) * kT - p.diag > 0));
+
+      mbar_wait(&bars[kBarQFull0 + st], (it >> 1) & 1);  // row statistics ride on the Q barrier
+      mbar_wait(&bars[kBarSFull], it & 1);
+      tc_fence_after();
+      float pr[64];
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        float s[32];
+        tmem_ld32(t_st + c * 32, reinterpret_cast<uint32_t*>(s));
+        tc_wait_ld();
+        uint32_t pk[16];
+#pragma unroll
+        for (int x4 = 0; x4 < 8; ++x4) {
+          const float4 l4 = *reinterpret_cast<const float4*>(ls + c * 32 + x4 * 4);
+          const float lv[4] = {l4.x, l4.y, l4.z, l4.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int x = x4 * 4 + e;
+            float pv = ex2(fmaf(s[x], p.scale_log2, -lv[e]));
+            if (need_mask) pv = (col_base + c * 32 + x >= c_min) ? pv : 0.f;
+            pr[c * 32 + x] = pv;
+          }
+        }
+#pragma unroll
+        for (int x = 0; x < 16; ++x) pk[x] = pack2<kBF16>(pr[c * 32 + 2 * x], pr[c * 32 + 2 * x + 1]);
+        tmem_st16(t_st + c * 16, pk);
+      }
+      tc_wait_st();
+      tc_fence_before();
+      mbar_arrive(&bars[kBarPReady]);
+
+      mbar_wait(&bars[kBarDPFull], it & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        float dp[32];
+        tmem_ld32(t_dpt + c * 32, reinterpret_cast<uint32_t*>(dp));
+        tc_wait_ld();
+        uint32_t pk[16];
+#pragma unroll
+        for (int x4 = 0; x4 < 8; ++x4) {
+          const float4 d4 = *reinterpret_cast<const float4*>(dl + c * 32 + x4 * 4);
+          const float dv4[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+          for (int e = 0; e < 4; e += 2) {
+            const int x = x4 * 4 + e;
+            const float a = pr[c * 32 + x] * (dp[x] - dv4[e]);
+            const float b = pr[c * 32 + x + 1] * (dp[x + 1] - dv4[e + 1]);
+            pk[x >> 1] = pack2<kBF16>(a, b);
+          }
+        }
+        tmem_st16(t_dpt + c * 16, pk);
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+          const int chunk = c * 4 + ch;
+          *reinterpret_cast<uint4*>(ds_row + ((chunk ^ (r & 7)) << 4)) =
+              make_uint4(pk[4 * ch], pk[4 * ch + 1], pk[4 * ch + 2], pk[4 * ch + 3]);
+        }
+      }
+      tc_wait_st();
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(&bars[kBarDSReady]);
+    }
+
+    // ------------------------------- epilogue: WG0 stores dV, WG1 stores dK * scale -------------------------------
+    if (n_iter > 0) {
+      mbar_wait(&bars[kBarDKVDone], 0);
+      tc_fence_after();
+    } else {
+      mbar_wait(&bars[kBarKV], 0);  // staging reuses the K/V tiles: their loads must have landed
+    }
+    uint8_t* stage_tile = wg == 0 ? v_smem : k_smem;
+    const uint32_t t_acc = tmem_base + lane_sel + (wg == 0 ? kColDV : kColDK);
+    const float mul = wg == 0 ? 1.f : p.scale;
+#pragma unroll
+    for (int q4 = 0; q4 < D / 32; ++q4) {
+      float a[32];
+      if (n_iter > 0) {
+        tmem_ld32(t_acc + q4 * 32, reinterpret_cast<uint32_t*>(a));
+        tc_wait_ld();
+      } else {
+#pragma unroll
+        for (int x = 0; x < 32; ++x) a[x] = 0.f;
+      }
+      uint32_t pk[16];
+#pragma unroll
+      for (int x = 0; x < 16; ++x) pk[x] = pack2<kBF16>(a[2 * x] * mul, a[2 * x + 1] * mul);
+      uint8_t* sub = stage_tile + (q4 >> 1) * kSub + r * 128;
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch) {
+        const int chunk = (q4 & 1) * 4 + ch;
+        *reinterpret_cast<uint4*>(sub + ((chunk ^ (r & 7)) << 4)) =
+            make_uint4(pk[4 * ch], pk[4 * ch + 1], pk[4 * ch + 2], pk[4 * ch + 3]);
+      }
+    }
+    fence_proxy_async_smem();
+    named_bar_sync(1 + wg, 128);
+    if (r == 0) {
+      const CUtensorMap* tm = wg == 0 ? &tm_dv : &tm_dk;
+      for (int ch = 0; ch < kChunks; ++ch) tma_store_3d(tm, stage_tile + ch * kSub, ch * 64, j * kT, bh);
+      tma_store_commit();
+      tma_store_wait_all<0>();
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 13) tmem_dealloc(tmem_base, 512);
+}
+
+// ------------------------------------------------------------------------------------------------
+// pre-pass: delta = rowsum(dO o O), packed with lse*log2e per 128-row tile (HBM-bound: 2*D*2 + 4 B read, 8 B written
+// per query row).  One warp handles 32/(D/8) rows at a time with 16-byte loads.
+// ------------------------------------------------------------------------------------------------
+template <int D, bool kBF16>
+__global__ void __launch_bounds__(256)
+fa_bwd_prepare_kernel(const uint16_t* __restrict__ o, const uint16_t* __restrict__ d_o, const float* __restrict__ lse,
+                      float* __restrict__ rowstats, long long n_q, long long bh, long long nqt, long long q_bh_stride,
+                      long long lse_bh_stride) {
+  constexpr int kLanesPerRow = D / 8;
+  constexpr int kRowsPerWarp = 32 / kLanesPerRow;
+  const int lane = threadIdx.x & 31;
+  const int sub = lane / kLanesPerRow, li = lane % kLanesPerRow;
+  const long long warp_global = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  const long long rows_pad = nqt * kT;
+  const long long total = bh * rows_pad;
+  for (long long r0 = warp_global * kRowsPerWarp; r0 < total; r0 += nwarps * kRowsPerWarp) {
+    const long long r = r0 + sub;  // padded row id (rows_pad is a multiple of kRowsPerWarp, so r < total)
+    const long long b = r / rows_pad, rr = r % rows_pad;
+    const bool valid = rr < n_q;
+    float acc = 0.f;
+    if (valid) {
+      const long long off = b * q_bh_stride + rr * D + li * 8;
+      const uint4 a = *reinterpret_cast<const uint4*>(o + off);
+      const uint4 g = *reinterpret_cast<const uint4*>(d_o + off);
+      const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, gw[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 x = unpack2<kBF16>(aw[e]), y = unpack2<kBF16>(gw[e]);
+        acc = fmaf(x.x, y.x, acc);
+        acc = fmaf(x.y, y.y, acc);
+      }
+    }
+#pragma unroll
+    for (int s = kLanesPerRow / 2; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+    if (li == 0) {
+      float l2 = INFINITY;  // padded rows and rows that saw no key: P = 2^(x - inf) = 0
+      if (valid) {
+        const float l = lse[b * lse_bh_stride + rr];
+        if (l != -INFINITY) l2 = l * 1.4426950408889634f;
+      }
+      float* tile = rowstats + (b * nqt + rr / kT) * 256;
+      tile[rr % kT] = l2;
+      tile[128 + rr % kT] = valid ? acc : 0.f;
+    }
+  }
+}
+
+template <int D, bool kBF16>
+static int launch_bwd(const Geometry& g, const void* q, const void* k, const void* v, const void* d_o,
+                      const float* rowstats, float* dq_accum, void* dk, void* dv, cudaStream_t stream) {
+  using Cfg = BwdCfg<D>;
+  const int elem = kBF16 ? kElemBF16 : kElemF16;
+  CUtensorMap tm_q, tm_k, tm_v, tm_do, tm_dq, tm_dk, tm_dv;
+  int rc;
+  if ((rc = make_tmap_3d(&tm_q, q, elem, D, g.n_q, g.bh, g.q_bh_stride, 64, kT))) return rc;
+  if ((rc = make_tmap_3d(&tm_do, d_o, elem, D, g.n_q, g.bh, g.q_bh_stride, 64, kT))) return rc;
+  if ((rc = make_tmap_3d(&tm_k, k, elem, D, g.n_kv, g.bh, g.kv_bh_stride, 64, kT))) return rc;
+  if ((rc = make_tmap_3d(&tm_v, v, elem, D, g.n_kv, g.bh, g.kv_bh_stride, 64, kT))) return rc;
+  if ((rc = make_tmap_3d(&tm_dk, dk, elem, D, g.n_kv, g.bh, g.kv_bh_stride, 64, kT))) return rc;
+  if ((rc = make_tmap_3d(&tm_dv, dv, elem, D, g.n_kv, g.bh, g.kv_bh_stride, 64, kT))) return rc;
+  if ((rc = make_tmap_3d(&tm_dq, dq_accum, kElemF32, D, g.n_q, g.bh, g.n_q * D, 32, kT))) return rc;
+
+  BwdParams p;
+  p.rowstats = rowstats;
+  p.n_q = static_cast<int>(g.n_q);
+  p.n_kv = static_cast<int>(g.n_kv);
+  p.bh = static_cast<int>(g.bh);
+  p.causal = g.causal;
+  p.diag = g.diag;
+  p.nqt = static_cast<int>((g.n_q + kT - 1) / kT);
+  p.nkt = static_cast<int>((g.n_kv + kT - 1) / kT);
+  p.scale = g.scale;
+  p.scale_log2 = g.scale * 1.4426950408889634f;
+
+  auto kern = fa_bwd_kernel<D, kBF16>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes) != cudaSuccess)
+      return FA_SM100_ELAUNCH;
+    attr_set = true;
+  }
+  const long long nblocks = static_cast<long long>(p.nkt) * g.bh;
+  if (nblocks > 0x7fffffffll) return FA_SM100_EINVAL_SHAPE;
+  kern<<<static_cast<unsigned>(nblocks), kBwdThreads, Cfg::kSmemBytes, stream>>>(tm_q, tm_k, tm_v, tm_do, tm_dq,
+                                                                                tm_dk, tm_dv, p);
+  return launch_status();
+}
+
+}  // namespace fa
+
+extern "C" size_t fa_sm100_rowstats_bytes(const fa_sm100_shape* s) {
+  if (!s || s->bh <= 0 || s->n_q <= 0) return 0;
+  const size_t nqt = static_cast<size_t>((s->n_q + fa::kT - 1) / fa::kT);
+  return static_cast<size_t>(s->bh) * nqt * 256 * sizeof(float);
+}
+
+extern "C" int fa_sm100_bwd_prepare(const fa_sm100_shape* s, const void* o, const void* d_o, const float* lse,
+                                    float* rowstats, void* stream) {
+  fa::Geometry g;
+  int rc = fa::check_shape(s, &g);
+  if (rc) return rc;
+  if (!fa::aligned16(o) || !fa::aligned16(d_o) || lse == nullptr || !fa::aligned16(rowstats))
+    return FA_SM100_EINVAL_PTR;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long long nqt = (g.n_q + fa::kT - 1) / fa::kT;
+  const long long rows = g.bh * nqt * fa::kT;
+  const int rows_per_block = (256 / 32) * (32 / (g.d / 8));
+  long long grid = (rows + rows_per_block - 1) / rows_per_block;
+  if (grid > 148 * 16) grid = 148 * 16;
+  const uint16_t* op = static_cast<const uint16_t*>(o);
+  const uint16_t* gp = static_cast<const uint16_t*>(d_o);
+  const bool bf = g.dtype == FA_SM100_DTYPE_BF16;
+#define FA_LAUNCH_PREP(DD, BF)                                                                                  \
+  fa::fa_bwd_prepare_kernel<DD, BF><<<static_cast<unsigned>(grid), 256, 0, st>>>(op, gp, lse, rowstats, g.n_q, g.bh, \
+                                                                                  nqt, g.q_bh_stride, g.lse_bh_stride)
+  if (g.d == 128) {
+    if (bf) FA_LAUNCH_PREP(128, true); else FA_LAUNCH_PREP(128, false);
+  } else {
+    if (bf) FA_LAUNCH_PREP(64, true); else FA_LAUNCH_PREP(64, false);
+  }
+#undef FA_LAUNCH_PREP
+  return fa::launch_status();
+}
+
+extern "C" int fa_sm100_bwd(const fa_sm100_shape* s, const void* q, const void* k, const void* v, const void* d_o,
+                            const float* rowstats, float* dq_accum, void* dk, void* dv, void* stream) {
+  fa::Geometry g;
+  int rc = fa::check_shape(s, &g);
+  if (rc) return rc;
+  if (!fa::aligned16(q) || !fa::aligned16(k) || !fa::aligned16(v) || !fa::aligned16(d_o) ||
+      !fa::aligned16(rowstats) || !fa::aligned16(dq_accum) || !fa::aligned16(dk) || !fa::aligned16(dv))
+    return FA_SM100_EINVAL_PTR;
+  if ((rc = fa::check_device())) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (g.d == 128) {
+    return g.dtype == FA_SM100_DTYPE_BF16 ? fa::launch_bwd<128, true>(g, q, k, v, d_o, rowstats, dq_accum, dk, dv, st)
+                                          : fa::launch_bwd<128, false>(g, q, k, v, d_o, rowstats, dq_accum, dk, dv, st);
+  }
+  return g.dtype == FA_SM100_DTYPE_BF16 ? fa::launch_bwd<64, true>(g, q, k, v, d_o, rowstats, dq_accum, dk, dv, st)
+                                        : fa::launch_bwd<64, false>(g, q, k, v, d_o, rowstats, dq_accum, dk, dv, st);
 }

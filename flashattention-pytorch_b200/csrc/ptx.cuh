@@ -100,6 +100,13 @@ __device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* m, const vo
                "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
                : "memory");
 }
+// 1-D bulk copy global -> shared (16-byte aligned, size a multiple of 16), completes on an mbarrier
+__device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(reinterpret_cast<uint64_t>(gmem_src)), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void tma_store_wait_read() {
@@ -193,8 +200,6 @@ __device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64
 // ------------------------------------------------------------------------------------------------
 // TMEM <-> registers.  Shape 32x32b: lane t of warp w touches TMEM lane 32*(w%4)+t, N consecutive columns.
 // ------------------------------------------------------------------------------------------------
-#define FA_R4(a, i) "%" #i ", %" #i "+1"  // (unused helper kept for grep-ability)
-
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"

@@ -60,8 +60,9 @@ ABI = {
     "fa_sm100_strerror": (ctypes.c_char_p, [ctypes.c_int]),
     "fa_sm100_dq_accum_bytes": (ctypes.c_size_t, [_SP]),
     "fa_sm100_fwd": (ctypes.c_int, [_SP, _P, _P, _P, _P, _P, _P, _P, _P]),
-    "fa_sm100_bwd_delta": (ctypes.c_int, [_SP, _P, _P, _P, _P]),
-    "fa_sm100_bwd": (ctypes.c_int, [_SP, _P, _P, _P, _P, _P, _P, _P, _P, _P, ctypes.c_int, _P]),
+    "fa_sm100_rowstats_bytes": (ctypes.c_size_t, [_SP]),
+    "fa_sm100_bwd_prepare": (ctypes.c_int, [_SP, _P, _P, _P, _P, _P]),
+    "fa_sm100_bwd": (ctypes.c_int, [_SP, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "fa_sm100_dq_finish": (ctypes.c_int, [_SP, _P, _P, _P]),
     "fa_sm100_cast_scaled": (ctypes.c_int, [_P, _P, ctypes.c_int64, ctypes.c_float, ctypes.c_int32, _P]),
     "fa_sm100_probe_umma": (ctypes.c_int, [ctypes.c_int, ctypes.c_int32, _P, _P, _P, _P]),
@@ -175,52 +176,56 @@ def fwd_raw(q, k, v, causal, softmax_scale, *, q_row0=0, kv_col0=0, out=None, ls
     return out, lse
 
 
-def bwd_raw(q, k, v, o, do, lse, causal, softmax_scale, *, q_row0=0, kv_col0=0, delta=None, dq_accum=None,
-            dkv_accum=None):
-    """Backward on padded/contiguous tensors.
+def bwd_prepare_raw(o, do, lse):
+    """Pre-pass of the backward: packs (lse * log2e, delta = rowsum(dO o O)) per 128-row query tile."""
+    lib = load_library()
+    bh, n_q, d = o.shape
+    shape = make_shape(bh, n_q, n_q, d, _dtype_code(o), False, 1.0)
+    rowstats = torch.empty(lib.fa_sm100_rowstats_bytes(ctypes.byref(shape)) // 4, device=o.device,
+                           dtype=torch.float32)
+    with torch.cuda.device(o.device):
+        _check(lib.fa_sm100_bwd_prepare(ctypes.byref(shape), o.data_ptr(), do.data_ptr(), lse.data_ptr(),
+                                        rowstats.data_ptr(), _stream_ptr(o)), "fa_sm100_bwd_prepare")
+    return rowstats
+
+
+def bwd_raw(q, k, v, o, do, lse, causal, softmax_scale, *, q_row0=0, kv_col0=0, rowstats=None, dq_accum=None):
+    """Backward on padded/contiguous tensors (d in {64,128}).
 
     Plain call: returns (dq, dk, dv) in the input dtype.
-    Ring call (``dq_accum`` fp32 (bh,n_q,d) and ``dkv_accum`` = (dk32, dv32) given): accumulates into them and
-    returns None — the caller finishes with ``dq_finish_raw`` / ``cast_scaled`` once the ring has gone round."""
+    Ring call (``dq_accum`` fp32 (bh,n_q,d) given, ``rowstats`` from ``bwd_prepare_raw``): dQ partials are added into
+    ``dq_accum`` (the caller finishes with ``dq_finish_raw`` after the last step) and (None, dk, dv) of THIS K/V
+    block is returned."""
     lib = load_library()
     bh, n_q, d = q.shape
     n_kv = k.shape[1]
     shape = make_shape(bh, n_q, n_kv, d, _dtype_code(q), causal, softmax_scale, q_row0, kv_col0)
     sp = ctypes.byref(shape)
     stream = _stream_ptr(q)
+    if rowstats is None:
+        rowstats = bwd_prepare_raw(o, do, lse)
+    ring = dq_accum is not None
+    if not ring:
+        dq_accum = torch.zeros((bh, n_q, d), device=q.device, dtype=torch.float32)
+    dk = torch.empty_like(k)
+    dv = torch.empty_like(v)
     with torch.cuda.device(q.device):
-        if delta is None:
-            delta = torch.empty((bh, n_q), device=q.device, dtype=torch.float32)
-            _check(lib.fa_sm100_bwd_delta(sp, o.data_ptr(), do.data_ptr(), delta.data_ptr(), stream),
-                   "fa_sm100_bwd_delta")
-        ring = dq_accum is not None
-        if not ring:
-            dq_accum = torch.zeros((bh, n_q, d), device=q.device, dtype=torch.float32)
-            dk = torch.empty_like(k)
-            dv = torch.empty_like(v)
-            acc_flag = 0
-        else:
-            dk, dv = dkv_accum
-            acc_flag = 1
-        _check(lib.fa_sm100_bwd(sp, q.data_ptr(), k.data_ptr(), v.data_ptr(), do.data_ptr(), lse.data_ptr(),
-                                delta.data_ptr(), dq_accum.data_ptr(), dk.data_ptr(), dv.data_ptr(), acc_flag,
-                                stream), "fa_sm100_bwd")
-        if ring:
-            return None
-        dq = torch.empty_like(q)
-        _check(lib.fa_sm100_dq_finish(sp, dq_accum.data_ptr(), dq.data_ptr(), stream), "fa_sm100_dq_finish")
-    return dq, dk, dv
+        _check(lib.fa_sm100_bwd(sp, q.data_ptr(), k.data_ptr(), v.data_ptr(), do.data_ptr(), rowstats.data_ptr(),
+                                dq_accum.data_ptr(), dk.data_ptr(), dv.data_ptr(), stream), "fa_sm100_bwd")
+    if ring:
+        return None, dk, dv
+    return dq_finish_raw(dq_accum, q.dtype, softmax_scale), dk, dv
 
 
-def delta_raw(o, do):
+def dq_finish_raw(dq_accum, dtype, softmax_scale):
     lib = load_library()
-    bh, n_q, d = o.shape
-    shape = make_shape(bh, n_q, n_q, d, _dtype_code(o), False, 1.0)
-    delta = torch.empty((bh, n_q), device=o.device, dtype=torch.float32)
-    with torch.cuda.device(o.device):
-        _check(lib.fa_sm100_bwd_delta(ctypes.byref(shape), o.data_ptr(), do.data_ptr(), delta.data_ptr(),
-                                      _stream_ptr(o)), "fa_sm100_bwd_delta")
-    return delta
+    bh, n_q, d = dq_accum.shape
+    shape = make_shape(bh, n_q, n_q, d, _DTYPES[dtype], False, softmax_scale)
+    dq = torch.empty((bh, n_q, d), device=dq_accum.device, dtype=dtype)
+    with torch.cuda.device(dq_accum.device):
+        _check(lib.fa_sm100_dq_finish(ctypes.byref(shape), dq_accum.data_ptr(), dq.data_ptr(),
+                                      _stream_ptr(dq_accum)), "fa_sm100_dq_finish")
+    return dq
 
 
 def cast_scaled(acc: torch.Tensor, alpha: float, dtype: torch.dtype) -> torch.Tensor:

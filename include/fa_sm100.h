@@ -4,7 +4,7 @@
  * This is the drop-in boundary for the reference's native extension.  The reference binds six functions on one
  * pybind11 module (reference csrc/common/torch.extension.cpp:73-83):
  *     fa1_forward / forward / fa3_forward      -> fa_sm100_fwd
- *     fa1_backward / backward / fa3_backward   -> fa_sm100_bwd_delta + fa_sm100_bwd + fa_sm100_dq_finish
+ *     fa1_backward / backward / fa3_backward   -> fa_sm100_bwd_prepare + fa_sm100_bwd + fa_sm100_dq_finish
  * FA1/FA2/FA3 are the same mathematical operator in the reference (csrc/fa1/fa1_fwd.cu:30-107,
  * csrc/fa2/fa2_fwd.cu:30-106, csrc/fa3/fa3_fwd.cu:103-211), so one kernel family serves all three.
  *
@@ -60,8 +60,11 @@ typedef struct fa_sm100_shape {
 int fa_sm100_version(void);
 const char* fa_sm100_strerror(int code);
 
-/* Scratch the caller must provide to fa_sm100_bwd: an fp32 dQ accumulator of bh * n_q * d elements. */
+/* Scratch the caller must provide to the backward:
+ *   dq_accum : fp32 dQ accumulator, bh * n_q * d elements, ZEROED by the caller before fa_sm100_bwd;
+ *   rowstats : per-query-row statistics packed per 128-row tile, bh * ceil(n_q/128) * 256 floats. */
 size_t fa_sm100_dq_accum_bytes(const fa_sm100_shape* s);
+size_t fa_sm100_rowstats_bytes(const fa_sm100_shape* s);
 
 /*
  * Forward.  Replaces fa{1,2,3}_forward (reference csrc/fa1/fa1_fwd.cu:30-107):
@@ -75,20 +78,23 @@ size_t fa_sm100_dq_accum_bytes(const fa_sm100_shape* s);
 int fa_sm100_fwd(const fa_sm100_shape* s, const void* q, const void* k, const void* v, void* o, float* lse,
                  const void* o_prev, const float* lse_prev, void* stream);
 
-/* Backward pre-pass: delta[bh, r] = sum_c dO[bh, r, c] * O[bh, r, c]  (reference csrc/fa1/fa1_bwd.cu:57). */
-int fa_sm100_bwd_delta(const fa_sm100_shape* s, const void* o, const void* d_o, float* delta, void* stream);
+/*
+ * Backward pre-pass (reference csrc/fa1/fa1_bwd.cu:57): delta[r] = sum_c dO[r,c] * O[r,c], packed together with
+ * lse[r] * log2(e) into `rowstats`: for slice b and 128-row tile t, floats [(b*T + t)*256, +128) hold lse*log2e and
+ * the next 128 hold delta (T = ceil(n_q/128)); rows past n_q get lse = +inf, delta = 0 so they contribute nothing.
+ * `lse` is the (bh, n_q) tensor the forward returned (lse_bh_stride applies).
+ */
+int fa_sm100_bwd_prepare(const fa_sm100_shape* s, const void* o, const void* d_o, const float* lse, float* rowstats,
+                         void* stream);
 
 /*
  * Backward main pass, KV-outer (reference csrc/fa1/fa1_bwd.cu:70-110 with the Python skip rule of
  * src/fa1/torch/impl.py:89): recomputes P = exp(S - lse), then
  *   dV = P^T dO,  dP = dO V^T,  dS = P o (dP - delta),  dK = scale * dS^T Q   -> dk, dv (input dtype)
- *   dQ partials (unscaled) are reduce-added in fp32 into dq_accum, which the caller zeroes beforehand.
- * If accumulate_dkv != 0, dk / dv are fp32 buffers of (bh, n_kv, d) and the results are ADDED to them
- * (ring attention backward, where dK/dV travel with their K/V block); otherwise they are written in `dtype`.
+ *   dQ partials (unscaled) are reduce-added in fp32 into dq_accum (see above).
  */
 int fa_sm100_bwd(const fa_sm100_shape* s, const void* q, const void* k, const void* v, const void* d_o,
-                 const float* lse, const float* delta, float* dq_accum, void* dk, void* dv, int accumulate_dkv,
-                 void* stream);
+                 const float* rowstats, float* dq_accum, void* dk, void* dv, void* stream);
 
 /* dq[i] = cast(dq_accum[i] * softmax_scale).  (The reference scales per tile: csrc/fa1/fa1_bwd.cu:102-103.) */
 int fa_sm100_dq_finish(const fa_sm100_shape* s, const float* dq_accum, void* dq, void* stream);

@@ -52,19 +52,92 @@ def stage_fwd(bh, n, d, dtype_name, causal):
     return 0 if ok else 1
 
 
+def stage_bwd(bh, n, d, dtype_name, causal):
+    import torch
+    import flashattention_lab_cuda as ext
+    from oracle.attention_oracle import dense_backward_fp32, error_report
+
+    dt = getattr(torch, dtype_name)
+    torch.manual_seed(4321)
+    q, k, v, do = (torch.randn(bh, n, d, device="cuda", dtype=dt) for _ in range(4))
+    o, lse = ext.fwd_raw(q, k, v, causal, d ** -0.5)
+    dq, dk, dv = ext.bwd_raw(q, k, v, o, do, lse, causal, d ** -0.5)
+    torch.cuda.synchronize()
+    dq_r, dk_r, dv_r, _, _ = dense_backward_fp32(q.cpu(), k.cpu(), v.cpu(), do.cpu(), causal, d ** -0.5)
+    ok = True
+    msg = []
+    for name, got, want in (("dQ", dq, dq_r), ("dK", dk, dk_r), ("dV", dv, dv_r)):
+        rep = error_report(got, want, 5e-2, 5e-2)
+        ok &= rep["violations"] == 0
+        msg.append(f"{name} max_abs={rep['max_abs']:.3e} viol={rep['violations']}")
+    print(f"bwd bh={bh} n={n} d={d} {dtype_name} causal={causal}: " + " | ".join(msg) + f" -> {'OK' if ok else 'FAIL'}",
+          flush=True)
+    return 0 if ok else 1
+
+
+def stage_perf(b, h, n, d, causal):
+    import torch
+    import flashattention_lab_cuda as ext
+
+    torch.manual_seed(0)
+    bh = b * h
+    q, k, v, do = (torch.randn(bh, n, d, device="cuda", dtype=torch.bfloat16) for _ in range(4))
+    scale = d ** -0.5
+    o, lse = ext.fwd_raw(q, k, v, causal, scale)
+    c = 0.5 if causal else 1.0
+    f_fwd = 4 * bh * n * n * d * c
+    f_bwd = 10 * bh * n * n * d * c
+
+    def timeit(fn, iters=10):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters
+
+    t_f = timeit(lambda: ext.fwd_raw(q, k, v, causal, scale, out=o, lse=lse))
+    line = f"perf B={b} H={h} N={n} d={d} causal={causal}: fwd {t_f:.3f} ms = {f_fwd / t_f / 1e9:.0f} TFLOP/s"
+    try:
+        t_b = timeit(lambda: ext.bwd_raw(q, k, v, o, do, lse, causal, scale))
+        line += f" | bwd(total) {t_b:.3f} ms = {f_bwd / t_b / 1e9:.0f} TFLOP/s"
+    except Exception as exc:  # noqa: BLE001
+        line += f" | bwd failed: {exc}"
+    print(line, flush=True)
+    return 0
+
+
 def main():
-    if len(sys.argv) > 1:
+    if len(sys.argv) > 1 and not sys.argv[1].startswith("--"):
         kind = sys.argv[1]
         if kind == "probe":
             sys.exit(stage_probe(int(sys.argv[2]), sys.argv[3]))
         if kind == "fwd":
             sys.exit(stage_fwd(int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]), sys.argv[5], sys.argv[6] == "1"))
+        if kind == "bwd":
+            sys.exit(stage_bwd(int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]), sys.argv[5], sys.argv[6] == "1"))
+        if kind == "perf":
+            sys.exit(stage_perf(int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]), int(sys.argv[5]), sys.argv[6] == "1"))
     stages = [["probe", str(m), dt] for m in range(4) for dt in ("bfloat16", "float16")]
     for bh, n, d, dt in [(1, 128, 128, "bfloat16"), (2, 256, 128, "bfloat16"), (2, 33, 64, "float16"),
                          (3, 300, 64, "float16"), (2, 1024, 128, "bfloat16"), (2, 777, 128, "float16"),
                          (4, 2048, 64, "bfloat16")]:
         for causal in ("0", "1"):
             stages.append(["fwd", str(bh), str(n), str(d), dt, causal])
+    if "--no-probe" in sys.argv or True:
+        stages = [st for st in stages if st[0] != "probe"] if "--skip-probe" in sys.argv else stages
+    for bh, n, d, dt in [(1, 128, 128, "bfloat16"), (2, 256, 128, "bfloat16"), (2, 33, 64, "float16"),
+                         (3, 300, 64, "float16"), (2, 1024, 128, "bfloat16"), (2, 777, 128, "float16"),
+                         (4, 2048, 64, "bfloat16")]:
+        for causal in ("0", "1"):
+            stages.append(["bwd", str(bh), str(n), str(d), dt, causal])
+    for b, h, n, d in [(4, 16, 4096, 128), (4, 16, 8192, 128), (4, 32, 4096, 64)]:
+        for causal in ("1", "0"):
+            stages.append(["perf", str(b), str(h), str(n), str(d), causal])
     fails = 0
     for st in stages:
         try:
