@@ -1,0 +1,147 @@
+"""CPU: the C-ABI library loads and exports every symbol include/fa_sm100.h declares; host-side logic of the
+reference-facing wrappers (no compute calls — there is no GPU here)."""
+import ctypes
+import re
+from pathlib import Path
+
+import pytest
+import torch
+
+ROOT = Path(__file__).resolve().parents[1]
+HEADER = (ROOT / "include" / "fa_sm100.h").read_text()
+
+
+def _declared_symbols():
+    return sorted(set(re.findall(r"\b(fa_sm100_[a-z0-9_]+)\s*\(", HEADER)) - {"fa_sm100_shape"})
+
+
+def test_header_declares_the_expected_surface():
+    syms = _declared_symbols()
+    for needed in ("fa_sm100_fwd", "fa_sm100_bwd", "fa_sm100_bwd_prepare", "fa_sm100_dq_finish", "fa_sm100_strerror"):
+        assert needed in syms
+
+
+def test_library_exports_every_declared_symbol():
+    import flashattention_lab_cuda as ext
+
+    path = ext.library_path()
+    assert path.exists(), f"{path} missing: run `python __graft_entry__.py`"
+    lib = ctypes.CDLL(str(path))
+    for name in _declared_symbols():
+        assert hasattr(lib, name), f"libfa_sm100.so does not export {name}"
+    assert set(ext.ABI) == set(_declared_symbols()), "shim ABI table and header disagree"
+
+
+def test_library_metadata_calls_work_without_gpu():
+    import flashattention_lab_cuda as ext
+
+    lib = ext.load_library()
+    assert lib.fa_sm100_version() >= 100
+    assert lib.fa_sm100_strerror(0) == b"ok"
+    assert b"head dim" in lib.fa_sm100_strerror(-2)
+    shape = ext.make_shape(bh=3, n_q=200, n_kv=200, d=128, dtype_code=1, causal=True, softmax_scale=0.1)
+    assert lib.fa_sm100_dq_accum_bytes(ctypes.byref(shape)) == 3 * 200 * 128 * 4
+    assert lib.fa_sm100_rowstats_bytes(ctypes.byref(shape)) == 3 * 2 * 256 * 4
+
+
+def test_argument_validation_happens_before_any_cuda_call():
+    import flashattention_lab_cuda as ext
+
+    lib = ext.load_library()
+    good = dict(bh=1, n_q=8, n_kv=8, d=64, dtype_code=0, causal=False, softmax_scale=1.0)
+    fake = ctypes.c_void_p(256)  # aligned non-null dummy; validation must fail before it is touched
+
+    def fwd(**over):
+        s = ext.make_shape(**{**good, **over})
+        return lib.fa_sm100_fwd(ctypes.byref(s), fake, fake, fake, fake, fake, None, None, None)
+
+    assert fwd(dtype_code=7) == -1
+    assert fwd(d=96) == -2
+    assert fwd(n_q=0) == -3
+    assert fwd(softmax_scale=0.0) == -5
+    s = ext.make_shape(**good)
+    assert lib.fa_sm100_fwd(ctypes.byref(s), None, fake, fake, fake, fake, None, None, None) == -4
+    assert lib.fa_sm100_fwd(ctypes.byref(s), ctypes.c_void_p(260), fake, fake, fake, fake, None, None, None) == -4
+
+
+def test_shape_struct_layout_matches_header():
+    import flashattention_lab_cuda as ext
+
+    # 3*8 + 3*4 + 4 + 5*8 = 80 bytes with natural alignment
+    assert ctypes.sizeof(ext._Shape) == 80
+    fields = [f[0] for f in ext._Shape._fields_]
+    order = re.findall(r"^\s+(?:int64_t|int32_t|float)\s+(\w+);", HEADER, flags=re.M)
+    assert fields == order
+
+
+@pytest.mark.parametrize("n", [1, 2, 3])
+def test_specs_match_reference_values(n):
+    mod = __import__(f"fa{n}.spec", fromlist=["x"])
+    pick = getattr(mod, f"pick_fa{n}_spec")
+    small, big = pick(64), pick(128)
+    assert (small.br, small.bc, small.num_warps) == (128, 128, 8)  # reference src/faN/spec.py
+    assert (big.br, big.bc, big.num_warps) == (64, 128, 8)
+    if n == 3:
+        assert small.stages == 2 and big.stages == 2
+    with pytest.raises(Exception):
+        small.br = 1  # frozen dataclass
+
+
+def test_merge_split_roundtrip():
+    from common.utils import merge_bh, split_bh, split_bh_lse
+
+    x = torch.arange(2 * 3 * 4 * 5.0).reshape(2, 3, 4, 5)
+    m, shp = merge_bh(x)
+    assert m.shape == (6, 4, 5) and shp == (2, 3)
+    assert torch.equal(split_bh(m, shp), x)
+    assert split_bh_lse(torch.zeros(6, 4), shp).shape == (2, 3, 4)
+    y, none = merge_bh(m)  # 3-D input: (tensor, None) — the reference's FA1/FA2 wrappers get this wrong (D6)
+    assert none is None and y is m
+
+
+@pytest.mark.parametrize("n", [1, 2, 3])
+def test_cpu_tensors_are_rejected_like_the_reference(n):
+    mod = __import__(f"fa{n}.op", fromlist=["x"])
+    attn = getattr(mod, f"fa{n}_attention")
+    q = torch.randn(1, 2, 8, 32)
+    with pytest.raises(RuntimeError, match="Inputs must be CUDA tensors"):  # reference src/fa2/cuda/impl.py:43-44
+        attn(q, q, q, backend="cuda")
+    with pytest.raises(RuntimeError, match="Inputs must be CUDA tensors"):
+        attn(q, q, q)  # "auto" no longer falls back to torch/triton
+    with pytest.raises(ValueError):
+        attn(q, q, q, backend="nope")  # reference src/fa2/op.py:29
+    for gone in ("triton", "torch"):
+        with pytest.raises(ValueError):
+            attn(q, q, q, backend=gone)
+
+
+def test_autograd_function_signatures():
+    import inspect
+
+    from fa1.cuda.impl import _FA1CudaFn
+    from fa2.cuda.impl import _FA2CudaFn
+    from fa3.cuda.impl import _FA3CudaFn
+
+    base = ["ctx", "q", "k", "v", "causal", "softmax_scale", "br", "bc"]
+    assert list(inspect.signature(_FA1CudaFn.forward).parameters) == base
+    assert list(inspect.signature(_FA2CudaFn.forward).parameters) == base
+    assert list(inspect.signature(_FA3CudaFn.forward).parameters) == base + ["stages", "fp8"]
+    for fn in (_FA1CudaFn, _FA2CudaFn, _FA3CudaFn):
+        assert list(inspect.signature(fn.backward).parameters) == ["ctx", "do", "dlse"]
+
+
+def test_extension_module_exports_reference_names():
+    import flashattention_lab_cuda as ext
+
+    for name in ("fa1_forward", "fa1_backward", "forward", "backward", "fa3_forward", "fa3_backward"):
+        assert callable(getattr(ext, name))  # reference csrc/common/torch.extension.cpp:73-83
+    with pytest.raises(NotImplementedError):
+        ext.fa3_forward(None, None, None, False, 1.0, 128, 128, 2, True)
+
+
+def test_product_path_never_imports_the_oracle():
+    pkg = ROOT / "flashattention-pytorch_b200"
+    for py in pkg.rglob("*.py"):
+        text = py.read_text()
+        assert "oracle" not in text.replace("oracle/", "").replace("the oracle", "") or "import oracle" not in text, py
+        assert "import oracle" not in text and "from oracle" not in text, f"{py} imports the oracle"
