@@ -1,0 +1,385 @@
+#!/usr/bin/env python
+"""bench.py — attention fwd+bwd throughput on B200 (the metric of BASELINE.json) and the reference CPU arm.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c4|headline]
+
+One "step" = one forward + one backward of `fa2_attention` (the reference's public entry point) over one batch of
+synthetic Q/K/V/dO.  Default workload at every N is BASELINE config C2 PER GPU (B=4 H=16 N=4096 d=128 bf16 causal):
+batch*head slices are independent, so N ranks simply own N times the slices — no data-path collective
+("scaling": "weak").  Prints ONE JSON line (rank 0).
+
+  value      whole-job fwd+bwd TFLOP/s, algorithmic FLOPs 14*B*H*N^2*d*(1/2 causal), inputs resident in HBM,
+             CUDA-event timed over exactly K steps, max over ranks.
+  e2e        the same metric through the public API with HOST (pinned) q/k/v/dO copied in and o/lse/dq/dk/dv copied
+             back inside the timed region of every step.
+  roofline   dominant kernel (the backward main kernel): algorithmic FLOPs / CUDA-event duration vs the measured
+             cuBLAS bf16 peak of MEASURED_PEAKS.json (fallback 1590 TFLOP/s of B200_PROFILING.md).
+  cpu_baseline  the oracle's CPU restatement ("port") timed on this box's host cores on a bounded sample.
+
+`--impl reference` times the reference's own native extension compiled for CPU (oracle/_ref, built from
+/root/reference/csrc by oracle/build_ref.py; falls back to the oracle port) on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path[:0] = [str(ROOT / "flashattention-pytorch_b200"), str(ROOT)]
+
+import torch  # noqa: E402
+
+WORKLOADS = {
+    # name: (B, H, N, d, causal)  — per GPU
+    "c2": (4, 16, 4096, 128, True),        # BASELINE configs[1]
+    "headline": (4, 16, 8192, 128, True),  # north-star "bf16 d=128 N=8K causal"
+    "c4": (32, 32, 8192, 128, True),       # BASELINE configs[3]: TOTAL shape, batch*head split over the ranks
+}
+NOMINAL_BF16_TFLOPS = 2250.0
+FALLBACK_BF16_TFLOPS = 1590.0
+
+
+def flops(b, h, n, d, causal):
+    c = 0.5 if causal else 1.0
+    f_fwd = 4.0 * b * h * n * n * d * c
+    return f_fwd, 2.5 * f_fwd
+
+
+def measured_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        j = json.loads(p.read_text())
+        return {"burst": float(j["bf16_tflops"]), "sustained": float(j.get("bf16_tflops_sustained", j["bf16_tflops"])),
+                "source": "measured"}
+    return {"burst": FALLBACK_BF16_TFLOPS, "sustained": 1400.0, "source": "fallback"}
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# clocks sampling (nvidia-smi during the timed region)
+# ----------------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc, self.thread = index, [], None, None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return None
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for ts, r in self.rows if t0 <= ts <= t1 + 0.2] or [r for _, r in self.rows]
+        if not rows:
+            return None
+        sm = [float(r[0]) for r in rows if r[0].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in rows for n, v in zip(names, r[3:7]) if v.lower().startswith("active")})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": float(rows[0][1]),
+                "power_w_max": max(float(r[2]) for r in rows), "samples": len(rows), "reasons": reasons}
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# CPU arms
+# ----------------------------------------------------------------------------------------------------------------------
+def _load_ref_ext():
+    so = sorted((ROOT / "oracle" / "_ref").glob("flashattention_lab_cuda_ref*.so"))
+    if not so:
+        return None
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("flashattention_lab_cuda_ref", so[0])
+    mod = importlib.util.module_from_spec(spec)
+    try:
+        spec.loader.exec_module(mod)
+    except Exception:  # noqa: BLE001  (ABI mismatch on another image -> fall back to the port)
+        return None
+    return mod
+
+
+def cpu_step_fn(kind, n, d, causal, bh_sample):
+    """Returns (callable running one fwd+bwd on the CPU over `bh_sample` slices, kind actually used)."""
+    g = torch.Generator().manual_seed(0)
+    q, k, v, do = (torch.randn((bh_sample, n, d), generator=g, dtype=torch.float32) for _ in range(4))
+    scale = d ** -0.5
+    ref = _load_ref_ext() if kind == "reference" else None
+    if ref is not None:
+        br, bc = (128, 128) if d <= 64 else (64, 128)  # reference src/fa2/spec.py
+
+        def step():
+            o, lse = ref.forward(q, k, v, causal, scale, br, bc)  # FA2 names, reference csrc/common/torch.extension.cpp:78-79
+            return ref.backward(q, k, v, o, do, lse, causal, scale, br, bc)
+
+        return step, "reference"
+    from oracle.attention_oracle import blocked_backward, blocked_forward
+
+    def step():
+        o, lse = blocked_forward(q, k, v, causal, scale)
+        return blocked_backward(q, k, v, o, do, lse, causal, scale)
+
+    return step, "port"
+
+
+def time_cpu(kind, workload, steps, warmup, budget_s=25.0):
+    b, h, n, d, causal = workload
+    bh_sample = 1
+    step, used = cpu_step_fn(kind, n, d, causal, bh_sample)
+    f_fwd, f_bwd = flops(1, bh_sample, n, d, causal)
+    t0 = time.perf_counter()
+    step()  # first call doubles as a cost probe
+    probe = time.perf_counter() - t0
+    steps = max(1, min(steps, int(budget_s / max(probe, 1e-3))))
+    warmup = max(0, min(warmup, int(budget_s / 4 / max(probe, 1e-3))))
+    for _ in range(warmup):
+        step()
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        step()
+        times.append(time.perf_counter() - t0)
+    mean = sum(times) / len(times)
+    return {"value": (f_fwd + f_bwd) / mean / 1e12, "unit": "TFLOP/s", "cores": torch.get_num_threads(),
+            "host_cpus": os.cpu_count(), "kind": used, "ms_per_step_sample": mean * 1e3, "steps": steps,
+            "sample": f"1 of {b * h} batch*head slices of the workload (N={n}, d={d}, causal={causal}, fp32 on CPU); "
+                      f"throughput is per-slice work / time, slices are independent"}
+
+
+def run_reference_arm(args, workload, name):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    b, h, n, d, causal = workload
+    res = time_cpu("reference", workload, args.steps, args.warmup)
+    line = {
+        "impl": "reference", "metric": "attention fwd+bwd TFLOP/s", "value": res["value"], "unit": "TFLOP/s",
+        "n_gpus": args.gpus, "steps": res["steps"], "warmup": args.warmup,
+        "ms_per_step": res["ms_per_step_sample"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": name, "B": b, "H": h, "N": n, "d": d, "causal": causal,
+                   "note": "reference csrc (ATen loops) compiled for CPU; its causal backward skips the wrong "
+                           "triangle (SURVEY D4) - same tile count, so the timing stands"},
+        "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": res["value"], "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------------------------------
+def run_ours(args, workload, name):
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    import flashattention_lab_cuda as ext
+    from fa2 import fa2_attention
+
+    ext.load_library()  # fail loudly if the CUDA library is missing
+    b, h, n, d, causal = workload
+    if name == "c4":  # total shape split over the ranks (strong scaling)
+        assert (b * h) % world == 0
+        b_local, h_local, scaling = 1, b * h // world, "strong"
+    else:
+        b_local, h_local, scaling = b, h, "weak"
+    f_fwd, f_bwd = flops(b_local, h_local, n, d, causal)
+    f_step = f_fwd + f_bwd
+    scale = d ** -0.5
+
+    g = torch.Generator(device=dev).manual_seed(rank)
+    shape = (b_local, h_local, n, d)
+    q, k, v = (torch.randn(shape, generator=g, device=dev, dtype=torch.bfloat16).requires_grad_(True) for _ in range(3))
+    do = torch.randn(shape, generator=g, device=dev, dtype=torch.bfloat16)
+
+    def step():
+        o, lse = fa2_attention(q, k, v, causal=causal, softmax_scale=scale, backend="cuda")
+        torch.autograd.backward(o, do)
+        q.grad = k.grad = v.grad = None
+        return o
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_wall0 = time.time()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    t_wall1 = time.time()
+    ms_total = e0.elapsed_time(e1)
+    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+    t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / args.steps
+    value = f_step * world / (ms_step * 1e-3) / 1e12
+
+    # ---------------- per-kernel timing on the launching stream (rank 0 reports) ----------------
+    qb, kb, vb, dob = (x.detach().reshape(b_local * h_local, n, d) for x in (q, k, v, do))
+    ob, lseb = ext.fwd_raw(qb, kb, vb, causal, scale)
+    rowstats = ext.bwd_prepare_raw(ob, dob, lseb)
+    dq_acc = torch.zeros((b_local * h_local, n, d), device=dev, dtype=torch.float32)
+
+    def time_kernel(fn, iters):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        a, bb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(iters):
+            fn()
+        bb.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(bb) / iters
+
+    iters = max(5, min(args.steps, 20))
+    t_fwd = time_kernel(lambda: ext.fwd_raw(qb, kb, vb, causal, scale, out=ob, lse=lseb), iters)
+    t_prep = time_kernel(lambda: ext.bwd_prepare_raw(ob, dob, lseb), iters)
+    t_bwd_main = time_kernel(lambda: ext.bwd_raw(qb, kb, vb, ob, dob, lseb, causal, scale, rowstats=rowstats,
+                                                 dq_accum=dq_acc), iters)
+    t_zero = time_kernel(lambda: dq_acc.zero_(), iters)
+    t_fin = time_kernel(lambda: ext.dq_finish_raw(dq_acc, torch.bfloat16, scale), iters)
+    peaks = measured_peaks()
+    ach_bwd = f_bwd / (t_bwd_main * 1e-3) / 1e12
+    traffic = None
+    tf = ROOT / "profiles" / "traffic.json"
+    if tf.exists():
+        try:
+            traffic = json.loads(tf.read_text()).get(name, {}).get("fa_bwd_kernel_dram_bytes_per_launch")
+        except Exception:  # noqa: BLE001
+            traffic = None
+    roofline = {"kernel": "fa_bwd_kernel<128,bf16>", "bound": "tensor", "achieved": ach_bwd, "peak": peaks["burst"],
+                "unit": "TFLOP/s", "frac": ach_bwd / peaks["burst"], "peak_source": peaks["source"] + " (burst)",
+                "frac_of_sustained": ach_bwd / peaks["sustained"], "frac_of_nominal": ach_bwd / NOMINAL_BF16_TFLOPS,
+                "algorithmic_flops_per_launch": f_bwd, "launch_ms": t_bwd_main, "traffic": traffic}
+    kernels = {
+        "fa_fwd_kernel": {"ms": t_fwd, "tflops": f_fwd / (t_fwd * 1e-3) / 1e12},
+        "fa_bwd_prepare_kernel": {"ms": t_prep},
+        "dq_accum_memset": {"ms": t_zero},
+        "fa_bwd_kernel": {"ms": t_bwd_main, "tflops": ach_bwd},
+        "fa_dq_finish_kernel": {"ms": t_fin},
+        "bwd_total_tflops": f_bwd / ((t_prep + t_zero + t_bwd_main + t_fin) * 1e-3) / 1e12,
+    }
+
+    # ---------------- end to end through the public API with host buffers ----------------
+    hq, hk, hv, hdo = (torch.randn(shape, dtype=torch.bfloat16).pin_memory() for _ in range(4))
+    ho, hdq, hdk, hdv = (torch.empty(shape, dtype=torch.bfloat16).pin_memory() for _ in range(4))
+    hlse = torch.empty(shape[:-1], dtype=torch.float32).pin_memory()
+    h2d = sum(x.numel() * x.element_size() for x in (hq, hk, hv, hdo))
+    d2h = sum(x.numel() * x.element_size() for x in (ho, hdq, hdk, hdv, hlse))
+
+    def e2e_step():
+        dq_, dk_, dv_ = (x.to(dev, non_blocking=True).requires_grad_(True) for x in (hq, hk, hv))
+        ddo = hdo.to(dev, non_blocking=True)
+        o, lse = fa2_attention(dq_, dk_, dv_, causal=causal, softmax_scale=scale, backend="cuda")
+        torch.autograd.backward(o, ddo)
+        ho.copy_(o.detach(), non_blocking=True)
+        hlse.copy_(lse.detach(), non_blocking=True)
+        hdq.copy_(dq_.grad, non_blocking=True)
+        hdk.copy_(dk_.grad, non_blocking=True)
+        hdv.copy_(dv_.grad, non_blocking=True)
+
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    e0.record()
+    for _ in range(e2e_steps):
+        e2e_step()
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t.item()) / e2e_steps
+    e2e = {"value": f_step * world / (e2e_ms * 1e-3) / 1e12, "unit": "TFLOP/s", "ms_per_step": e2e_ms,
+           "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps}
+
+    if rank == 0:
+        cpu = time_cpu("port", workload, 3, 1) if world == 1 else None
+        line = {
+            "metric": "attention fwd+bwd TFLOP/s", "value": value, "unit": "TFLOP/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": scaling, "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": name, "B_per_gpu": b_local, "H_per_gpu": h_local, "N": n, "d": d, "causal": causal,
+                       "parallelism": f"batch*head sharded x{world}, no collective",
+                       "flop_convention": "14*B*H*N^2*d*(0.5 if causal)", "l2": "inputs (q,k,v,do = 4x64 MiB at c2) "
+                       "exceed the 126 MB L2; no explicit flush"},
+            "frac_of_nominal_bf16_peak": value / world / NOMINAL_BF16_TFLOPS,
+            "frac_of_measured_bf16_peak": value / world / peaks["burst"],
+            "clocks": clocks, "e2e": e2e, "gpu_launches": 4 * args.steps, "roofline": roofline, "kernels": kernels,
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    args = ap.parse_args()
+    workload = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference_arm(args, workload, args.workload)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the sm_100a path has no CPU fallback (use --impl reference)")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.gpus > 1 and world == 1:
+        # convenience: re-launch under torchrun when called directly with --gpus N
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 1000), __file__,
+               "--gpus", str(args.gpus), "--steps", str(args.steps), "--warmup", str(args.warmup),
+               "--workload", args.workload]
+        raise SystemExit(subprocess.call(cmd))
+    run_ours(args, workload, args.workload)
+
+
+if __name__ == "__main__":
+    main()
