@@ -75,7 +75,7 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kOffBars);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kBarCount);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = static_cast<int>(warp_uniform(threadIdx.x >> 5));
   const int lane = threadIdx.x & 31;
 
   const int bh = blockIdx.x / p.nkt;
@@ -112,7 +112,7 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = warp_uniform(*tmem_slot);
   constexpr uint32_t kColST = 0, kColDPT = 128, kColDV = 256, kColDK = 256 + D;
 
   if (warp == 12) {
@@ -140,7 +140,7 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
     __syncwarp();
   } else if (warp == 13) {
     // ===================================== MMA issuer =====================================
-    if (lane == 0 && n_iter > 0) {
+    if (n_iter > 0) {  // whole warp runs the loop; only the tcgen05 instructions are elected
       constexpr uint32_t idesc_s = umma_idesc(kBF16, kT, kT, false, false);
       constexpr uint32_t idesc_acc = umma_idesc(kBF16, kT, D, false, true);
       constexpr uint32_t idesc_dq = umma_idesc(kBF16, kT, D, true, true);
@@ -152,8 +152,9 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
 #pragma unroll
         for (int kk = 0; kk < D / 16; ++kk) {
           const uint32_t off = (kk >> 2) * kSub + (kk & 3) * 32;
-          umma_ss(tmem_base + d_col, umma_smem_desc(a_base + off, 16, 1024), umma_smem_desc(b_base + off, 16, 1024),
-                  idesc_s, kk > 0 ? 1u : 0u);
+          if (elect_one())
+            umma_ss(tmem_base + d_col, umma_smem_desc(a_base + off, 16, 1024), umma_smem_desc(b_base + off, 16, 1024),
+                    idesc_s, kk > 0 ? 1u : 0u);
         }
       };
       // D[kv, d] (+)= A^T-in-TMEM[kv, q] . B[q, d]   (contraction over the 128 query rows; B MN-major)
@@ -162,16 +163,18 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
 #pragma unroll
         for (int kk = 0; kk < kT / 16; ++kk) {
           const uint32_t a = tmem_base + a_col + (kk < 4 ? kk * 8 : 64 + (kk - 4) * 8);
-          umma_ts(tmem_base + d_col, a, umma_smem_desc(b_base + kk * 16 * 128, kSub, 1024), idesc_acc,
-                  (acc || kk > 0) ? 1u : 0u);
+          if (elect_one())
+            umma_ts(tmem_base + d_col, a, umma_smem_desc(b_base + kk * 16 * 128, kSub, 1024), idesc_acc,
+                    (acc || kk > 0) ? 1u : 0u);
         }
       };
       // dQ[q, d] = dS[q, kv] . K[kv, d]   (contraction over the 128 kv rows; both operands MN-major)
       auto mma_dq = [&]() {
 #pragma unroll
         for (int kk = 0; kk < kT / 16; ++kk) {
-          umma_ss(tmem_base + kColDPT, umma_smem_desc(ds_addr + kk * 16 * 128, kT * 128, 1024),
-                  umma_smem_desc(k_addr + kk * 16 * 128, kSub, 1024), idesc_dq, kk > 0 ? 1u : 0u);
+          if (elect_one())
+            umma_ss(tmem_base + kColDPT, umma_smem_desc(ds_addr + kk * 16 * 128, kT * 128, 1024),
+                    umma_smem_desc(k_addr + kk * 16 * 128, kSub, 1024), idesc_dq, kk > 0 ? 1u : 0u);
         }
       };
 
@@ -179,40 +182,40 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
       mbar_wait(&bars[kBarQFull0], 0);
       tc_fence_after();
       mma_kmajor(kColST, k_addr, q_addr);
-      tc_commit(&bars[kBarSFull]);
+      tc_commit_elect(&bars[kBarSFull]);
       mbar_wait(&bars[kBarDOFull], 0);
       tc_fence_after();
       mma_kmajor(kColDPT, v_addr, do_addr);
-      tc_commit(&bars[kBarDPFull]);
+      tc_commit_elect(&bars[kBarDPFull]);
 
       for (int it = 0; it < n_iter; ++it) {
         const int st = it & 1;
         mbar_wait(&bars[kBarPReady], it & 1);
         tc_fence_after();
         mma_from_tmem(kColDV, kColST, do_addr, it > 0);
-        tc_commit(&bars[kBarDOEmpty]);
+        tc_commit_elect(&bars[kBarDOEmpty]);
 
         mbar_wait(&bars[kBarDSReady], it & 1);
         tc_fence_after();
         mma_from_tmem(kColDK, kColDPT, q_addr + st * Cfg::kTileBytes, it > 0);
-        tc_commit(&bars[kBarQEmpty0 + st]);
+        tc_commit_elect(&bars[kBarQEmpty0 + st]);
         mma_dq();
-        tc_commit(&bars[kBarDQFull]);
+        tc_commit_elect(&bars[kBarDQFull]);
 
         if (it + 1 < n_iter) {
           const int nst = st ^ 1;
           mbar_wait(&bars[kBarQFull0 + nst], ((it + 1) >> 1) & 1);
           tc_fence_after();
           mma_kmajor(kColST, k_addr, q_addr + nst * Cfg::kTileBytes);
-          tc_commit(&bars[kBarSFull]);
+          tc_commit_elect(&bars[kBarSFull]);
           mbar_wait(&bars[kBarDOFull], (it + 1) & 1);
           mbar_wait(&bars[kBarDQDrained], it & 1);
           tc_fence_after();
           mma_kmajor(kColDPT, v_addr, do_addr);
-          tc_commit(&bars[kBarDPFull]);
+          tc_commit_elect(&bars[kBarDPFull]);
         }
       }
-      tc_commit(&bars[kBarDKVDone]);
+      tc_commit_elect(&bars[kBarDKVDone]);
     }
     __syncwarp();
   } else if (warp >= 8) {

@@ -9,11 +9,14 @@
 //   warps 0-3  : softmax warpgroup for query tile 0 (thread t owns row t: TMEM lane == row, no shuffles)
 //   warps 4-7  : softmax warpgroup for query tile 1
 //   warp  8    : TMA producer (Q once, then K_0 V_0 K_1 V_1 ... through an NS-deep ring)
-//   warp  9    : MMA issuer (one lane), owns the TMEM allocation
+//   warps 9,10 : MMA issuers, one per query tile (independent issue streams); warp 9 owns the TMEM allocation
 // TMEM (512 columns x 128 lanes, fp32):  [0,128) S0   [128,256) S1   [256,256+D) O0   [256+D,256+2D) O1
-//   P_i (16-bit) overwrites columns [0,64) of S_i and is consumed straight from TMEM (tcgen05.mma A-in-TMEM).
-// The tensor pipe executes MMAs in issue order, so "P_i V_j ; Q_i K_{j+1}^T" needs no barrier in between even though
-// S_i(j+1) overwrites P_i(j); while it runs, the other warpgroup does its softmax.
+// The softmax works in STEPS of 64 key columns; each query tile's 128 S columns are two 64-column buffers, so
+// S_i(t+1) is already in TMEM while the warpgroup is still exponentiating S_i(t) and never waits for the tensor pipe:
+//   step t (KV tile t/2, half t%2, buffer t%2):  S_i(t) = Q_i K[half]^T  ->  P_i(t) (16-bit, first 32 columns of the
+//   buffer, consumed straight from TMEM as the A operand)  ->  O_i += P_i(t) V[half]  ->  S_i(t+2) into the same buffer.
+// The tensor pipe executes MMAs in issue order, so "P_i(t) V ; Q_i K(t+2)^T" needs no barrier in between even though
+// S_i(t+2) overwrites P_i(t).
 #include "ptx.cuh"
 #include "fa_host.cuh"
 
@@ -30,8 +33,9 @@ struct FwdParams {
 };
 
 constexpr int kBM = 128;  // query rows per tile
-constexpr int kBN = 128;  // key rows per tile
-constexpr int kFwdThreads = 320;
+constexpr int kBN = 128;  // key rows per K/V tile (TMA granularity)
+constexpr int kStep = 64;  // key columns per softmax step
+constexpr int kFwdThreads = 352;  // 8 softmax warps + producer + one MMA warp per query tile
 constexpr float kRescaleThreshold = 8.0f;  // lazy O rescale: only when the row max grows by > 2^8
 
 template <int D>
@@ -42,14 +46,14 @@ struct FwdCfg {
   static constexpr int kSmemBytes = 2 * kTileBytes + kStages * kTileBytes + 1024 /*align*/ + 256 /*barriers*/;
 };
 
-// number of KV tiles a query tile starting at local row `row0` must visit
-__device__ __forceinline__ int fwd_num_kv_tiles(int row0, const FwdParams& p) {
+// number of 64-column softmax steps a query tile starting at local row `row0` must visit
+__device__ __forceinline__ int fwd_num_steps(int row0, const FwdParams& p) {
   if (row0 >= p.n_q) return 0;
-  int n = (p.n_kv + kBN - 1) / kBN;
+  int n = (p.n_kv + kStep - 1) / kStep;
   if (p.causal) {
     const long long last_visible = static_cast<long long>(row0) + kBM - 1 + p.diag;  // for the tile's last row
     if (last_visible < 0) return 0;
-    const int nc = static_cast<int>(last_visible / kBN) + 1;
+    const int nc = static_cast<int>(last_visible / kStep) + 1;
     n = nc < n ? nc : n;
   }
   return n;
@@ -69,35 +73,39 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
   uint8_t* q_smem = smem;                            // 2 tiles
   uint8_t* kv_smem = smem + 2 * Cfg::kTileBytes;     // NS tiles
   uint64_t* bars = reinterpret_cast<uint64_t*>(kv_smem + NS * Cfg::kTileBytes);
-  uint64_t* q_full = bars;            // [2]
-  uint64_t* s_full = bars + 2;        // [2]  MMA -> softmax: S_i(j) is in TMEM
-  uint64_t* p_ready = bars + 4;       // [2]  softmax -> MMA: P_i(j) stored (and O_i rescaled)
-  uint64_t* pv_done = bars + 6;       // [2]  MMA -> softmax: O_i += P_i(j) V_j finished
-  uint64_t* kv_full = bars + 8;       // [NS]
-  uint64_t* kv_empty = bars + 8 + NS; // [NS]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8 + 2 * NS);
+  uint64_t* q_full = bars;             // [2]
+  uint64_t* s_full = bars + 2;         // [2 tiles][2 buffers]  MMA -> softmax: S_i(t) is in TMEM
+  uint64_t* p_ready = bars + 6;        // [2][2]  softmax -> MMA: P_i(t) stored (and O_i rescaled)
+  uint64_t* pv_done = bars + 10;       // [2][2]  MMA -> softmax: O_i += P_i(t) V finished (indexed by t&1, see below)
+  uint64_t* kv_full = bars + 14;       // [NS]
+  uint64_t* kv_empty = bars + 14 + NS; // [NS]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14 + 2 * NS);
+  // pv_done is split by step parity so that every barrier a warpgroup waits on is at most ONE phase behind what it
+  // already knows to be complete: s_full(t) only proves PV(t-2) finished, and a parity wait cannot tell "two phases
+  // behind" from "done".
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = static_cast<int>(warp_uniform(threadIdx.x >> 5));
   const int lane = threadIdx.x & 31;
 
   // heavy (late, for causal) tile pairs first; all pairs of one slice adjacent so its K/V stay L2-resident
   const int bh = blockIdx.x / p.npairs;
   const int pair = p.npairs - 1 - (blockIdx.x % p.npairs);
   const int row0_t0 = pair * 2 * kBM;
-  const int nt0 = fwd_num_kv_tiles(row0_t0, p);
-  const int nt1 = fwd_num_kv_tiles(row0_t0 + kBM, p);
-  const int ntmax = nt0 > nt1 ? nt0 : nt1;
+  const int nt0 = fwd_num_steps(row0_t0, p);
+  const int nt1 = fwd_num_steps(row0_t0 + kBM, p);
+  const int ntmax = nt0 > nt1 ? nt0 : nt1;   // steps
+  const int n_kv_tiles = (ntmax + 1) >> 1;   // 128-row K/V tiles to stream
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&q_full[i], 1);
+    for (int i = 0; i < 2; ++i) mbar_init(&q_full[i], 1);
+    for (int i = 0; i < 4; ++i) {
       mbar_init(&s_full[i], 1);
       mbar_init(&p_ready[i], 128);
       mbar_init(&pv_done[i], 1);
     }
     for (int i = 0; i < NS; ++i) {
       mbar_init(&kv_full[i], 1);
-      mbar_init(&kv_empty[i], 1);
+      mbar_init(&kv_empty[i], 2);  // both MMA warps release every stage
     }
     fence_mbar_init();
   }
@@ -114,7 +122,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = warp_uniform(*tmem_slot);
 
   if (warp == 8) {
     // ===================================== TMA producer =====================================
@@ -124,7 +132,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
         for (int c = 0; c < kChunks; ++c)
           tma_load_3d(q_smem + i * Cfg::kTileBytes + c * kSub, &tm_q, &q_full[i], c * 64, row0_t0 + i * kBM, bh);
       }
-      for (int t = 0; t < 2 * ntmax; ++t) {
+      for (int t = 0; t < 2 * n_kv_tiles; ++t) {
         const int stage = t % NS;
         mbar_wait(&kv_empty[stage], ((t / NS) & 1) ^ 1);
         mbar_arrive_expect_tx(&kv_full[stage], Cfg::kTileBytes);
@@ -134,79 +142,86 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
       }
     }
     __syncwarp();
-  } else if (warp == 9) {
-    // ===================================== MMA issuer =====================================
-    if (lane == 0 && ntmax > 0) {
-      constexpr uint32_t idesc_s = umma_idesc(kBF16, kBM, kBN, false, false);  // S = Q K^T : A, B K-major
-      constexpr uint32_t idesc_o = umma_idesc(kBF16, kBM, D, false, true);     // O += P V : A in TMEM, B MN-major
-      const uint32_t q_addr = smem_u32(q_smem);
-      const uint32_t kv_addr = smem_u32(kv_smem);
-      const int nt[2] = {nt0, nt1};
+  } else if (warp >= 9) {
+    // ===================================== MMA issuers (warp 9 -> tile 0, warp 10 -> tile 1) =====================
+    // Whole warp runs the loop (uniform control flow, descriptors in uniform registers); one elected lane issues.
+    // Every warp walks EVERY ring slot (wait full -> use -> release), even past its own tile's last step, so the
+    // two-arrival kv_empty barriers stay in lock-step with the producer.
+    const int i = warp - 9;
+    const int nti = i == 0 ? nt0 : nt1;
+    if (ntmax > 0) {
+      constexpr uint32_t idesc_s = umma_idesc(kBF16, kBM, kStep, false, false);  // S = Q K^T : A, B K-major
+      constexpr uint32_t idesc_o = umma_idesc(kBF16, kBM, D, false, true);       // O += P V : A in TMEM, B MN-major
+      constexpr uint32_t kStageLo = Cfg::kTileBytes >> 4;                         // descriptor units per ring stage
+      constexpr uint32_t kHalfLo = (kStep * 128) >> 4;                            // second 64 key rows of a tile
+      const uint32_t q_lo = umma_desc_lo(smem_u32(q_smem) + i * Cfg::kTileBytes, 16);
+      const uint32_t k_lo0 = umma_desc_lo(smem_u32(kv_smem), 16);                 // K as K-major B operand
+      const uint32_t v_lo0 = umma_desc_lo(smem_u32(kv_smem), kSub);               // V as MN-major B operand
+      const uint32_t t_s = tmem_base + i * kBN;
+      const uint32_t t_o = tmem_base + 256 + i * D;
 
-      auto issue_s = [&](int i, int stage) {
-        const uint32_t a0 = q_addr + i * Cfg::kTileBytes;
-        const uint32_t b0 = kv_addr + stage * Cfg::kTileBytes;
+      auto issue_s = [&](int step, uint32_t stage) {  // S_i(step) into buffer step&1
+        const uint32_t b_lo = k_lo0 + stage * kStageLo + (step & 1) * kHalfLo;
+        const uint32_t d_tmem = t_s + (step & 1) * kStep;
 #pragma unroll
         for (int kk = 0; kk < D / 16; ++kk) {
-          const uint32_t off = (kk >> 2) * kSub + (kk & 3) * 32;  // 16 elements = 32 B inside the 128-B swizzle row
-          umma_ss(tmem_base + i * kBN, umma_smem_desc(a0 + off, 16, 1024), umma_smem_desc(b0 + off, 16, 1024),
-                  idesc_s, kk > 0 ? 1u : 0u);
+          constexpr uint32_t kSubLo = Cfg::kSubTileBytes >> 4;
+          const uint32_t off = (kk >> 2) * kSubLo + (kk & 3) * 2;  // 16 elements = 32 B inside the 128-B swizzle row
+          umma_ss(d_tmem, umma_desc(q_lo + off), umma_desc(b_lo + off), idesc_s, kk > 0 ? 1u : 0u);
         }
       };
-      auto issue_pv = [&](int i, int stage, bool acc) {
-        const uint32_t b0 = kv_addr + stage * Cfg::kTileBytes;
+      auto issue_pv = [&](int step, uint32_t stage, bool acc) {  // O_i += P_i(step) V[half]
+        const uint32_t b_lo = v_lo0 + stage * kStageLo + (step & 1) * kHalfLo;
+        const uint32_t a_tmem = t_s + (step & 1) * kStep;
 #pragma unroll
-        for (int kk = 0; kk < kBN / 16; ++kk) {
-          // A: 16 key columns of P = 8 TMEM columns (two 16-bit values per column).  B: 16 key rows of V.
-          umma_ts(tmem_base + 256 + i * D, tmem_base + i * kBN + kk * 8,
-                  umma_smem_desc(b0 + kk * 16 * 128, kSub, 1024), idesc_o, (acc || kk > 0) ? 1u : 0u);
-        }
+        for (int kk = 0; kk < kStep / 16; ++kk)  // A: 16 key columns = 8 TMEM columns; B: 16 key rows = 2 KiB
+          umma_ts(t_o, a_tmem + kk * 8, umma_desc(b_lo + kk * 128), idesc_o, (acc || kk > 0) ? 1u : 0u);
       };
-      auto stage_of = [&](int t) { return t % NS; };
-      auto phase_of = [&](int t) { return (t / NS) & 1; };
+      // ring slot of K tile j is 2j, of V tile j is 2j+1; NS is a power of two
+      static_assert((NS & (NS - 1)) == 0, "ring depth must be a power of two");
+      auto stage_of = [&](uint32_t slot) { return slot & (NS - 1); };
+      auto phase_of = [&](uint32_t slot) { return (slot / NS) & 1u; };
 
-      mbar_wait(&q_full[0], 0);
-      mbar_wait(&q_full[1], 0);
-      mbar_wait(&kv_full[stage_of(0)], phase_of(0));
+      mbar_wait(&q_full[i], 0);
+      mbar_wait(&kv_full[0], 0);
       tc_fence_after();
-      for (int i = 0; i < 2; ++i) {
-        if (nt[i] > 0) {
-          issue_s(i, stage_of(0));
-          tc_commit(&s_full[i]);
+      if (elect_one()) {
+        if (0 < nti) {
+          issue_s(0, 0);
+          tc_commit(&s_full[i * 2]);
         }
+        if (1 < nti) {
+          issue_s(1, 0);
+          tc_commit(&s_full[i * 2 + 1]);
+        }
+        tc_commit(&kv_empty[0]);  // K tile 0 only feeds steps 0 and 1
       }
-      tc_commit(&kv_empty[stage_of(0)]);
+      __syncwarp();
 
-      for (int j = 0; j < ntmax; ++j) {
-        const int tv = 2 * j + 1, tk = 2 * j + 2;
-        const bool has_next = (j + 1 < ntmax);
-        mbar_wait(&kv_full[stage_of(tv)], phase_of(tv));
-        bool k_ready = false;
-        for (int i = 0; i < 2; ++i) {
-          if (j < nt[i]) {
-            mbar_wait(&p_ready[i], j & 1);
-            tc_fence_after();
-            issue_pv(i, stage_of(tv), j > 0);
-            tc_commit(&pv_done[i]);
+      for (int t = 0; t < ntmax; ++t) {
+        const uint32_t sv = 2 * (t >> 1) + 1;  // ring slot of the V tile of step t
+        const int s2 = t + 2;                  // the S step issued in this iteration
+        const uint32_t sk = 2 * (s2 >> 1);     // ring slot of its K tile
+        if ((t & 1) == 0) mbar_wait(&kv_full[stage_of(sv)], phase_of(sv));
+        if ((s2 & 1) == 0 && s2 < ntmax) mbar_wait(&kv_full[stage_of(sk)], phase_of(sk));
+        if (t < nti) mbar_wait(&p_ready[i * 2 + (t & 1)], (t >> 1) & 1);
+        tc_fence_after();
+        if (elect_one()) {
+          if (t < nti) {
+            issue_pv(t, stage_of(sv), t > 0);
+            tc_commit(&pv_done[i * 2 + (t & 1)]);
           }
-          if (j + 1 < nt[i]) {
-            if (!k_ready) {
-              mbar_wait(&kv_full[stage_of(tk)], phase_of(tk));
-              tc_fence_after();
-              k_ready = true;
-            }
-            issue_s(i, stage_of(tk));
-            tc_commit(&s_full[i]);
+          if (s2 < nti) {
+            issue_s(s2, stage_of(sk));
+            tc_commit(&s_full[i * 2 + (s2 & 1)]);
           }
+          // V tile: released after its second half (or the very last step); K tile: after its odd (or last) S step
+          if ((t & 1) == 1 || t == ntmax - 1) tc_commit(&kv_empty[stage_of(sv)]);
+          if (s2 <= ntmax - 1 && ((s2 & 1) == 1 || s2 == ntmax - 1)) tc_commit(&kv_empty[stage_of(sk)]);
         }
-        tc_commit(&kv_empty[stage_of(tv)]);
-        if (has_next) {
-          if (!k_ready) mbar_wait(&kv_full[stage_of(tk)], phase_of(tk));
-          tc_commit(&kv_empty[stage_of(tk)]);
-        }
+        __syncwarp();
       }
     }
-    __syncwarp();
   } else {
     // ===================================== softmax warpgroups =====================================
     const int wg = warp >> 2;            // query tile 0 / 1
@@ -228,24 +243,26 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
     float m_ref = -INFINITY;  // reference max (raw score units) all stored exponentials are relative to
     float l_sum = 0.f;
 
-    for (int j = 0; j < nt; ++j) {
-      mbar_wait(&s_full[wg], j & 1);
+    for (int j = 0; j < nt; ++j) {  // j = 64-column step
+      const int buf = j & 1;
+      const uint32_t t_sb = t_s + buf * kStep;
+      mbar_wait(&s_full[wg * 2 + buf], (j >> 1) & 1);
       tc_fence_after();
-      float s[kBN];
-#pragma unroll
-      for (int q4 = 0; q4 < kBN / 32; ++q4) tmem_ld32(t_s + q4 * 32, reinterpret_cast<uint32_t*>(s) + q4 * 32);
+      float s[kStep];
+      tmem_ld32(t_sb, reinterpret_cast<uint32_t*>(s));
+      tmem_ld32(t_sb + 32, reinterpret_cast<uint32_t*>(s) + 32);
       tc_wait_ld();
 
-      const long long lim_ll = vis - static_cast<long long>(j) * kBN;
-      if (lim_ll < kBN - 1) {
+      const long long lim_ll = vis - static_cast<long long>(j) * kStep;
+      if (lim_ll < kStep - 1) {
         const int lim = lim_ll < -1 ? -1 : static_cast<int>(lim_ll);
 #pragma unroll
-        for (int x = 0; x < kBN; ++x) s[x] = (x > lim) ? -INFINITY : s[x];
+        for (int x = 0; x < kStep; ++x) s[x] = (x > lim) ? -INFINITY : s[x];
       }
 
       float mx0 = s[0], mx1 = s[1], mx2 = s[2], mx3 = s[3];
 #pragma unroll
-      for (int x = 4; x < kBN; x += 4) {
+      for (int x = 4; x < kStep; x += 4) {
         mx0 = fmaxf(mx0, s[x]);
         mx1 = fmaxf(mx1, s[x + 1]);
         mx2 = fmaxf(mx2, s[x + 2]);
@@ -270,10 +287,10 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
       }
       const float mc = ((m_ref == -INFINITY) ? 0.f : m_ref) * c;
 
-      // P = 2^(S*c - m*c), row-sum in fp32, stored 16-bit into the first 64 columns of S
+      // P = 2^(S*c - m*c), row-sum in fp32, stored 16-bit into the first 32 columns of this S buffer
       float ls0 = 0.f, ls1 = 0.f;
 #pragma unroll
-      for (int q2 = 0; q2 < kBN / 32; ++q2) {
+      for (int q2 = 0; q2 < kStep / 32; ++q2) {
         uint32_t pk[16];
 #pragma unroll
         for (int x = 0; x < 16; ++x) {
@@ -283,12 +300,12 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
           ls1 += p1;
           pk[x] = pack2<kBF16>(p0, p1);
         }
-        tmem_st16(t_s + q2 * 16, pk);
+        tmem_st16(t_sb + q2 * 16, pk);
       }
       l_sum += ls0 + ls1;
 
       if (rescale) {  // warp-uniform
-        mbar_wait(&pv_done[wg], (j - 1) & 1);
+        mbar_wait(&pv_done[wg * 2 + ((j - 1) & 1)], ((j - 1) >> 1) & 1);
         tc_fence_after();
 #pragma unroll
         for (int q4 = 0; q4 < D / 32; ++q4) {
@@ -302,12 +319,13 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
       }
       tc_wait_st();
       tc_fence_before();
-      mbar_arrive(&p_ready[wg]);
+      mbar_arrive(&p_ready[wg * 2 + buf]);
     }
 
     // ------------------------------- epilogue: O / l, lse, optional LSE merge, TMA store -------------------------------
     if (nt > 0) {
-      mbar_wait(&pv_done[wg], (nt - 1) & 1);
+      if (nt > 1) mbar_wait(&pv_done[wg * 2 + ((nt - 2) & 1)], ((nt - 2) >> 1) & 1);
+      mbar_wait(&pv_done[wg * 2 + ((nt - 1) & 1)], ((nt - 1) >> 1) & 1);
       tc_fence_after();
     } else {
       mbar_wait(&q_full[wg], 0);  // the Q buffer doubles as the O staging tile: its TMA load must have landed

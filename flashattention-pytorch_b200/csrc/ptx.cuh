@@ -17,6 +17,23 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// One elected lane of a fully converged warp.  Keeping the surrounding control flow warp-uniform (all 32 lanes run the
+// loops, only the tcgen05 instruction itself is elected) lets the compiler keep descriptors and TMEM addresses in
+// uniform registers; issuing from inside a divergent `lane == 0` branch costs R2UR moves and a uniformisation loop
+// per MMA (~160 cycles each, measured in round 1).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ uint32_t warp_uniform(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
+
 // Hang guard: a blocked barrier wait traps after ~4 s instead of wedging the GPU.
 #ifndef FA_WAIT_TIMEOUT_CYCLES
 #define FA_WAIT_TIMEOUT_CYCLES (8000000000ll)
@@ -143,6 +160,12 @@ __device__ __forceinline__ void tc_commit(uint64_t* bar) {
                : "memory");
 }
 
+// warp-uniform call site: one elected lane commits (must be the lane that issued the MMAs: elect.sync is stable)
+__device__ __forceinline__ void tc_commit_elect(uint64_t* bar) {
+  if (elect_one()) tc_commit(bar);
+  __syncwarp();
+}
+
 // ------------------------------------------------------------------------------------------------
 // UMMA descriptors
 // ------------------------------------------------------------------------------------------------
@@ -161,6 +184,16 @@ __host__ __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr, 
   d |= static_cast<uint64_t>(1) << 46;  // descriptor version (Blackwell)
   d |= static_cast<uint64_t>(2) << 61;  // SWIZZLE_128B
   return d;
+}
+
+// Split form for hot loops: the high word is a compile-time constant, the low word is (addr >> 4) | (LBO >> 4) << 16,
+// so advancing an operand is one 32-bit add on the low word (smem addresses are < 2^18, no carry into the LBO field).
+constexpr uint32_t kDescHiSw128 = (1024u >> 4) | (1u << 14) | (2u << 29);  // SBO = 1024 B, version 1, SWIZZLE_128B
+__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t smem_addr, uint32_t lbo_bytes) {
+  return ((smem_addr >> 4) & 0x3FFFu) | ((lbo_bytes >> 4) << 16);
+}
+__device__ __forceinline__ uint64_t umma_desc(uint32_t lo) {
+  return (static_cast<uint64_t>(kDescHiSw128) << 32) | lo;
 }
 
 // Instruction descriptor for kind::f16 (fp16/bf16 operands, fp32 accumulate).

@@ -125,7 +125,8 @@ def main():
     stages = [["probe", str(m), dt] for m in range(4) for dt in ("bfloat16", "float16")]
     for bh, n, d, dt in [(1, 128, 128, "bfloat16"), (2, 256, 128, "bfloat16"), (2, 33, 64, "float16"),
                          (3, 300, 64, "float16"), (2, 1024, 128, "bfloat16"), (2, 777, 128, "float16"),
-                         (4, 2048, 64, "bfloat16")]:
+                         (4, 2048, 64, "bfloat16"), (8, 4096, 128, "bfloat16"), (150, 1536, 128, "float16"),
+                         (2, 8192, 64, "float16")]:
         for causal in ("0", "1"):
             stages.append(["fwd", str(bh), str(n), str(d), dt, causal])
     if "--no-probe" in sys.argv or True:
@@ -138,6 +139,9 @@ def main():
     for b, h, n, d in [(4, 16, 4096, 128), (4, 16, 8192, 128), (4, 32, 4096, 64)]:
         for causal in ("1", "0"):
             stages.append(["perf", str(b), str(h), str(n), str(d), causal])
+    only = [a.split("=", 1)[1].split(",") for a in sys.argv if a.startswith("--only=")]
+    if only:
+        stages = [st for st in stages if st[0] in only[0]]
     fails = 0
     for st in stages:
         try:
