@@ -37,6 +37,10 @@ constexpr int kBN = 128;  // key rows per K/V tile (TMA granularity)
 constexpr int kStep = 64;  // key columns per softmax step
 constexpr int kFwdThreads = 352;  // 8 softmax warps + producer + one MMA warp per query tile
 constexpr float kRescaleThreshold = 8.0f;  // lazy O rescale: only when the row max grows by > 2^8
+#ifndef FA_FWD_EMU_OF8
+#define FA_FWD_EMU_OF8 0
+#endif
+constexpr int kEmuOf8 = FA_FWD_EMU_OF8;  // element pairs (of every 8) exponentiated on the FMA pipe instead of MUFU
 
 template <int D>
 struct FwdCfg {
@@ -287,22 +291,30 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
       }
       const float mc = ((m_ref == -INFINITY) ? 0.f : m_ref) * c;
 
-      // P = 2^(S*c - m*c), row-sum in fp32, stored 16-bit into the first 32 columns of this S buffer
-      float ls0 = 0.f, ls1 = 0.f;
+      // P = 2^(S*c - m*c), row-sum in fp32, stored 16-bit into the first 32 columns of this S buffer.
+      // MUFU (16 ex2/clk/SM) is the co-bottleneck of the tensor pipe at d=128, so kEmuOf8 of every 8 element pairs
+      // take the polynomial path on the FMA pipe instead; all arithmetic is packed fp32x2.
+      float2 ls_a = make_float2(0.f, 0.f), ls_b = make_float2(0.f, 0.f);
+      const float2 c2 = make_float2(c, c), nmc2 = make_float2(-mc, -mc);
 #pragma unroll
       for (int q2 = 0; q2 < kStep / 32; ++q2) {
         uint32_t pk[16];
 #pragma unroll
         for (int x = 0; x < 16; ++x) {
-          const float p0 = ex2(fmaf(s[q2 * 32 + 2 * x], c, -mc));
-          const float p1 = ex2(fmaf(s[q2 * 32 + 2 * x + 1], c, -mc));
-          ls0 += p0;
-          ls1 += p1;
-          pk[x] = pack2<kBF16>(p0, p1);
+          const float2 t = ffma2(make_float2(s[q2 * 32 + 2 * x], s[q2 * 32 + 2 * x + 1]), c2, nmc2);
+          float2 pv;
+          if ((x & 7) < kEmuOf8) {
+            pv = ex2_poly2(t);
+          } else {
+            pv.x = ex2(t.x);
+            pv.y = ex2(t.y);
+          }
+          if (x & 1) ls_b = fadd2(ls_b, pv); else ls_a = fadd2(ls_a, pv);
+          pk[x] = pack2<kBF16>(pv.x, pv.y);
         }
         tmem_st16(t_sb + q2 * 16, pk);
       }
-      l_sum += ls0 + ls1;
+      l_sum += (ls_a.x + ls_a.y) + (ls_b.x + ls_b.y);
 
       if (rescale) {  // warp-uniform
         mbar_wait(&pv_done[wg * 2 + ((j - 1) & 1)], ((j - 1) >> 1) & 1);

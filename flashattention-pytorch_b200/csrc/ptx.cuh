@@ -281,6 +281,44 @@ __device__ __forceinline__ float ex2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// ---- packed fp32x2 arithmetic (sm_100 FFMA2 / FADD2): two lanes per issue slot on the FMA pipe ----
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  uint64_t ra, rb, rc, rd;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rc) : "f"(c.x), "f"(c.y));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+  float2 d;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+  return d;
+}
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+  uint64_t ra, rb, rd;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+  float2 d;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+  return d;
+}
+// 2^t for a pair on the FMA/ALU pipes instead of MUFU: Cody-Waite split t = n + f (n = round(t), |f| <= 0.5),
+// degree-3 minimax for 2^f (max rel. error 7.5e-5, far below the 16-bit rounding of P), exponent spliced in with an
+// integer shift-add.  Valid for t <= 127; t is clamped at -126 (result ~1e-38, i.e. zero for the softmax).
+__device__ __forceinline__ float2 ex2_poly2(float2 t) {
+  constexpr float kMagic = 12582912.f;  // 1.5 * 2^23: adding it rounds to the nearest integer in the low mantissa bits
+  t.x = fmaxf(t.x, -126.f);
+  t.y = fmaxf(t.y, -126.f);
+  const float2 r = fadd2(t, make_float2(kMagic, kMagic));
+  const float2 rf = fadd2(r, make_float2(-kMagic, -kMagic));
+  const float2 f = ffma2(rf, make_float2(-1.f, -1.f), t);
+  float2 p = ffma2(f, make_float2(0.0551716685f, 0.0551716685f), make_float2(0.2426111251f, 0.2426111251f));
+  p = ffma2(p, f, make_float2(0.6932609677f, 0.6932609677f));
+  p = ffma2(p, f, make_float2(0.9999280572f, 0.9999280572f));
+  p.x = __int_as_float(__float_as_int(p.x) + (__float_as_int(r.x) << 23));
+  p.y = __int_as_float(__float_as_int(p.y) + (__float_as_int(r.y) << 23));
+  return p;
+}
+
 // pack two fp32 -> one 32-bit word of two 16-bit floats; `lo` lands in the low half (= even element index)
 template <bool kBF16>
 __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
