@@ -13,6 +13,9 @@
 //   dK  += dS^T Q      (A = dS^T in TMEM,     B = Q  smem MN-major)           -> TMEM DK
 //   dQ   = dS   K      (A = dS^T smem read MN-major, B = K smem MN-major)     -> TMEM DPT (aliases dP^T/dS^T)
 // TMEM columns: ST [0,128)  DPT [128,256)  DV [256,256+D)  DK [256+D,256+2D).
+// MMA issue order per query tile i:   dV(i) . dP^T(i) . S^T(i+1) . dK(i) . dQ(i)
+//   so the exponentials of tile i+1 (need S^T(i+1)) overlap dK(i)/dQ(i) on the tensor pipe, the dS phase of tile i
+//   (needs dP^T(i)) overlaps S^T(i+1), and the dQ(i-1) drain has a whole dV slot before dP^T(i) reuses its columns.
 //
 // Warps: 0-3 / 4-7 compute warpgroups (thread = kv row; WG0 takes query columns 0-63, WG1 64-127),
 //        8-11 dQ drain warpgroup (TMEM -> swizzled smem -> TMA reduce-add, thread = query row),
@@ -23,7 +26,7 @@
 namespace fa {
 
 struct BwdParams {
-  const float* rowstats;  // (bh, nqt, 2, 128): lse*log2e then delta, per 128-row query tile
+  const float* rowstats;  // (bh, nqt, 2, 128): -lse*log2e then -delta, per 128-row query tile
   int n_q, n_kv, bh, causal, diag, nqt, nkt;
   float scale_log2, scale;
 };
@@ -140,80 +143,85 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
     __syncwarp();
   } else if (warp == 13) {
     // ===================================== MMA issuer =====================================
-    if (n_iter > 0) {  // whole warp runs the loop; only the tcgen05 instructions are elected
+    if (n_iter > 0) {  // whole warp runs the loop (uniform control flow); one elected lane issues
       constexpr uint32_t idesc_s = umma_idesc(kBF16, kT, kT, false, false);
       constexpr uint32_t idesc_acc = umma_idesc(kBF16, kT, D, false, true);
       constexpr uint32_t idesc_dq = umma_idesc(kBF16, kT, D, true, true);
-      const uint32_t k_addr = smem_u32(k_smem), v_addr = smem_u32(v_smem), q_addr = smem_u32(q_smem),
-                     do_addr = smem_u32(do_smem), ds_addr = smem_u32(ds_smem);
+      constexpr uint32_t kSubLo = kSub >> 4, kTileLo = Cfg::kTileBytes >> 4;
+      // low descriptor words: K-major views (LBO unused = 16 B) and MN-major views (LBO = next 64-column sub-tile)
+      const uint32_t k_km = umma_desc_lo(smem_u32(k_smem), 16), v_km = umma_desc_lo(smem_u32(v_smem), 16);
+      const uint32_t q_km = umma_desc_lo(smem_u32(q_smem), 16), do_km = umma_desc_lo(smem_u32(do_smem), 16);
+      const uint32_t k_mn = umma_desc_lo(smem_u32(k_smem), kSub), q_mn = umma_desc_lo(smem_u32(q_smem), kSub);
+      const uint32_t do_mn = umma_desc_lo(smem_u32(do_smem), kSub), ds_mn = umma_desc_lo(smem_u32(ds_smem), kT * 128);
 
       // D[kv, q] = A[kv, :] . B[q, :]   (both K-major, contraction over the head dim)
-      auto mma_kmajor = [&](uint32_t d_col, uint32_t a_base, uint32_t b_base) {
+      auto mma_kmajor = [&](uint32_t d_col, uint32_t a_lo, uint32_t b_lo) {
 #pragma unroll
         for (int kk = 0; kk < D / 16; ++kk) {
-          const uint32_t off = (kk >> 2) * kSub + (kk & 3) * 32;
-          if (elect_one())
-            umma_ss(tmem_base + d_col, umma_smem_desc(a_base + off, 16, 1024), umma_smem_desc(b_base + off, 16, 1024),
-                    idesc_s, kk > 0 ? 1u : 0u);
+          const uint32_t off = (kk >> 2) * kSubLo + (kk & 3) * 2;
+          umma_ss(tmem_base + d_col, umma_desc(a_lo + off), umma_desc(b_lo + off), idesc_s, kk > 0 ? 1u : 0u);
         }
       };
       // D[kv, d] (+)= A^T-in-TMEM[kv, q] . B[q, d]   (contraction over the 128 query rows; B MN-major)
       // the 16-bit A operand sits in columns [0,32) (queries 0-63, written by WG0) and [64,96) (queries 64-127, WG1)
-      auto mma_from_tmem = [&](uint32_t d_col, uint32_t a_col, uint32_t b_base, bool acc) {
+      auto mma_from_tmem = [&](uint32_t d_col, uint32_t a_col, uint32_t b_lo, bool acc) {
 #pragma unroll
         for (int kk = 0; kk < kT / 16; ++kk) {
           const uint32_t a = tmem_base + a_col + (kk < 4 ? kk * 8 : 64 + (kk - 4) * 8);
-          if (elect_one())
-            umma_ts(tmem_base + d_col, a, umma_smem_desc(b_base + kk * 16 * 128, kSub, 1024), idesc_acc,
-                    (acc || kk > 0) ? 1u : 0u);
+          umma_ts(tmem_base + d_col, a, umma_desc(b_lo + kk * 128), idesc_acc, (acc || kk > 0) ? 1u : 0u);
         }
       };
       // dQ[q, d] = dS[q, kv] . K[kv, d]   (contraction over the 128 kv rows; both operands MN-major)
       auto mma_dq = [&]() {
 #pragma unroll
-        for (int kk = 0; kk < kT / 16; ++kk) {
-          if (elect_one())
-            umma_ss(tmem_base + kColDPT, umma_smem_desc(ds_addr + kk * 16 * 128, kT * 128, 1024),
-                    umma_smem_desc(k_addr + kk * 16 * 128, kSub, 1024), idesc_dq, kk > 0 ? 1u : 0u);
-        }
+        for (int kk = 0; kk < kT / 16; ++kk)
+          umma_ss(tmem_base + kColDPT, umma_desc(ds_mn + kk * 128), umma_desc(k_mn + kk * 128), idesc_dq,
+                  kk > 0 ? 1u : 0u);
       };
 
       mbar_wait(&bars[kBarKV], 0);
       mbar_wait(&bars[kBarQFull0], 0);
       tc_fence_after();
-      mma_kmajor(kColST, k_addr, q_addr);
-      tc_commit_elect(&bars[kBarSFull]);
-      mbar_wait(&bars[kBarDOFull], 0);
-      tc_fence_after();
-      mma_kmajor(kColDPT, v_addr, do_addr);
-      tc_commit_elect(&bars[kBarDPFull]);
+      if (elect_one()) {
+        mma_kmajor(kColST, k_km, q_km);
+        tc_commit(&bars[kBarSFull]);
+      }
+      __syncwarp();
 
       for (int it = 0; it < n_iter; ++it) {
-        const int st = it & 1;
+        const uint32_t st = it & 1;
+        // ---- dV(it) += P^T dO ; dP^T(it) = V dO^T
+        mbar_wait(&bars[kBarDOFull], it & 1);
         mbar_wait(&bars[kBarPReady], it & 1);
+        if (it > 0) mbar_wait(&bars[kBarDQDrained], (it - 1) & 1);  // dP^T reuses the dQ(it-1) columns
         tc_fence_after();
-        mma_from_tmem(kColDV, kColST, do_addr, it > 0);
-        tc_commit_elect(&bars[kBarDOEmpty]);
-
+        if (elect_one()) {
+          mma_from_tmem(kColDV, kColST, do_mn, it > 0);
+          mma_kmajor(kColDPT, v_km, do_km);
+          tc_commit(&bars[kBarDPFull]);
+          tc_commit(&bars[kBarDOEmpty]);
+        }
+        __syncwarp();
+        // ---- S^T(it+1) = K Q^T  (P^T(it) in the S columns has been consumed by dV(it): in-order tensor pipe)
+        if (it + 1 < n_iter) {
+          mbar_wait(&bars[kBarQFull0 + (st ^ 1)], ((it + 1) >> 1) & 1);
+          tc_fence_after();
+          if (elect_one()) {
+            mma_kmajor(kColST, k_km, q_km + (st ^ 1) * kTileLo);
+            tc_commit(&bars[kBarSFull]);
+          }
+          __syncwarp();
+        }
+        // ---- dK(it) += dS^T Q ; dQ(it) = dS K
         mbar_wait(&bars[kBarDSReady], it & 1);
         tc_fence_after();
-        mma_from_tmem(kColDK, kColDPT, q_addr + st * Cfg::kTileBytes, it > 0);
-        tc_commit_elect(&bars[kBarQEmpty0 + st]);
-        mma_dq();
-        tc_commit_elect(&bars[kBarDQFull]);
-
-        if (it + 1 < n_iter) {
-          const int nst = st ^ 1;
-          mbar_wait(&bars[kBarQFull0 + nst], ((it + 1) >> 1) & 1);
-          tc_fence_after();
-          mma_kmajor(kColST, k_addr, q_addr + nst * Cfg::kTileBytes);
-          tc_commit_elect(&bars[kBarSFull]);
-          mbar_wait(&bars[kBarDOFull], (it + 1) & 1);
-          mbar_wait(&bars[kBarDQDrained], it & 1);
-          tc_fence_after();
-          mma_kmajor(kColDPT, v_addr, do_addr);
-          tc_commit_elect(&bars[kBarDPFull]);
+        if (elect_one()) {
+          mma_from_tmem(kColDK, kColDPT, q_mn + st * kTileLo, it > 0);
+          tc_commit(&bars[kBarQEmpty0 + st]);
+          mma_dq();
+          tc_commit(&bars[kBarDQFull]);
         }
+        __syncwarp();
       }
       tc_commit_elect(&bars[kBarDKVDone]);
     }
@@ -264,8 +272,8 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
 
     for (int it = 0; it < n_iter; ++it) {
       const int i = i_min + it, st = it & 1;
-      const float* ls = stats_smem + st * 256 + col_base;  // lse * log2e for this WG's 64 query columns
-      const float* dl = ls + 128;                          // delta
+      const float* ls = stats_smem + st * 256 + col_base;  // -lse * log2e for this WG's 64 query columns
+      const float* dl = ls + 128;                          // -delta
       // key (j*128 + r) is visible to query (i*128 + c) iff c >= c_min
       // ... and keys past n_kv (zero-filled by TMA) are never visible
       const bool kv_tail = (j * kT + kT > p.n_kv);
@@ -277,6 +285,7 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
       mbar_wait(&bars[kBarSFull], it & 1);
       tc_fence_after();
       float pr[64];
+      const float2 c2 = make_float2(p.scale_log2, p.scale_log2);
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         float s[32];
@@ -285,14 +294,15 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
         uint32_t pk[16];
 #pragma unroll
         for (int x4 = 0; x4 < 8; ++x4) {
-          const float4 l4 = *reinterpret_cast<const float4*>(ls + c * 32 + x4 * 4);
-          const float lv[4] = {l4.x, l4.y, l4.z, l4.w};
+          const float4 l4 = *reinterpret_cast<const float4*>(ls + c * 32 + x4 * 4);  // -lse * log2e
+          const float2 t0 = ffma2(make_float2(s[x4 * 4], s[x4 * 4 + 1]), c2, make_float2(l4.x, l4.y));
+          const float2 t1 = ffma2(make_float2(s[x4 * 4 + 2], s[x4 * 4 + 3]), c2, make_float2(l4.z, l4.w));
+          float pv[4] = {ex2(t0.x), ex2(t0.y), ex2(t1.x), ex2(t1.y)};
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const int x = x4 * 4 + e;
-            float pv = ex2(fmaf(s[x], p.scale_log2, -lv[e]));
-            if (need_mask) pv = (col_base + c * 32 + x >= c_min) ? pv : 0.f;
-            pr[c * 32 + x] = pv;
+            if (need_mask) pv[e] = (col_base + c * 32 + x >= c_min) ? pv[e] : 0.f;
+            pr[c * 32 + x] = pv[e];
           }
         }
 #pragma unroll
@@ -313,15 +323,14 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
         uint32_t pk[16];
 #pragma unroll
         for (int x4 = 0; x4 < 8; ++x4) {
-          const float4 d4 = *reinterpret_cast<const float4*>(dl + c * 32 + x4 * 4);
-          const float dv4[4] = {d4.x, d4.y, d4.z, d4.w};
-#pragma unroll
-          for (int e = 0; e < 4; e += 2) {
-            const int x = x4 * 4 + e;
-            const float a = pr[c * 32 + x] * (dp[x] - dv4[e]);
-            const float b = pr[c * 32 + x + 1] * (dp[x + 1] - dv4[e + 1]);
-            pk[x >> 1] = pack2<kBF16>(a, b);
-          }
+          const float4 d4 = *reinterpret_cast<const float4*>(dl + c * 32 + x4 * 4);  // -delta
+          const int x = x4 * 4;
+          const float2 a = fmul2(make_float2(pr[c * 32 + x], pr[c * 32 + x + 1]),
+                                 fadd2(make_float2(dp[x], dp[x + 1]), make_float2(d4.x, d4.y)));
+          const float2 b = fmul2(make_float2(pr[c * 32 + x + 2], pr[c * 32 + x + 3]),
+                                 fadd2(make_float2(dp[x + 2], dp[x + 3]), make_float2(d4.z, d4.w)));
+          pk[x >> 1] = pack2<kBF16>(a.x, a.y);
+          pk[(x >> 1) + 1] = pack2<kBF16>(b.x, b.y);
         }
         tmem_st16(t_dpt + c * 16, pk);
 #pragma unroll
@@ -420,14 +429,14 @@ fa_bwd_prepare_kernel(const uint16_t* __restrict__ o, const uint16_t* __restrict
 #pragma unroll
     for (int s = kLanesPerRow / 2; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
     if (li == 0) {
-      float l2 = INFINITY;  // padded rows and rows that saw no key: P = 2^(x - inf) = 0
+      float nl2 = -INFINITY;  // padded rows and rows that saw no key: P = 2^(x - inf) = 0
       if (valid) {
         const float l = lse[b * lse_bh_stride + rr];
-        if (l != -INFINITY) l2 = l * 1.4426950408889634f;
+        if (l != -INFINITY) nl2 = -l * 1.4426950408889634f;
       }
       float* tile = rowstats + (b * nqt + rr / kT) * 256;
-      tile[rr % kT] = l2;
-      tile[128 + rr % kT] = valid ? acc : 0.f;
+      tile[rr % kT] = nl2;                      // stored negated: the main kernel folds them in with one FMA / ADD
+      tile[128 + rr % kT] = valid ? -acc : 0.f;
     }
   }
 }

@@ -301,6 +301,15 @@ __device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
   asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
   return d;
 }
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+  uint64_t ra, rb, rd;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+  float2 d;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+  return d;
+}
 // 2^t for a pair on the FMA/ALU pipes instead of MUFU: Cody-Waite split t = n + f (n = round(t), |f| <= 0.5),
 // degree-3 minimax for 2^f (max rel. error 7.5e-5, far below the 16-bit rounding of P), exponent spliced in with an
 // integer shift-add.  Valid for t <= 127; t is clamped at -126 (result ~1e-38, i.e. zero for the softmax).

@@ -80,8 +80,8 @@ int fa_sm100_fwd(const fa_sm100_shape* s, const void* q, const void* k, const vo
 
 /*
  * Backward pre-pass (reference csrc/fa1/fa1_bwd.cu:57): delta[r] = sum_c dO[r,c] * O[r,c], packed together with
- * lse[r] * log2(e) into `rowstats`: for slice b and 128-row tile t, floats [(b*T + t)*256, +128) hold lse*log2e and
- * the next 128 hold delta (T = ceil(n_q/128)); rows past n_q get lse = +inf, delta = 0 so they contribute nothing.
+ * lse[r] * log2(e) into `rowstats`, both NEGATED: for slice b and 128-row tile t, floats [(b*T + t)*256, +128) hold
+ * -lse*log2e and the next 128 hold -delta (T = ceil(n_q/128)); rows past n_q get -inf / 0 so they contribute nothing.
  * `lse` is the (bh, n_q) tensor the forward returned (lse_bh_stride applies).
  */
 int fa_sm100_bwd_prepare(const fa_sm100_shape* s, const void* o, const void* d_o, const float* lse, float* rowstats,
