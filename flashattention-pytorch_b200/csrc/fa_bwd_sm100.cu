@@ -13,13 +13,14 @@
 //   dK  += dS^T Q      (A = dS^T in TMEM,     B = Q  smem MN-major)           -> TMEM DK
 //   dQ   = dS   K      (A = dS^T smem read MN-major, B = K smem MN-major)     -> TMEM DPT (aliases dP^T/dS^T)
 // TMEM columns: ST [0,128)  DPT [128,256)  DV [256,256+D)  DK [256+D,256+2D).
-// MMA issue order per query tile i:   dV(i) . dP^T(i) . S^T(i+1) . dK(i) . dQ(i)
-//   so the exponentials of tile i+1 (need S^T(i+1)) overlap dK(i)/dQ(i) on the tensor pipe, the dS phase of tile i
-//   (needs dP^T(i)) overlaps S^T(i+1), and the dQ(i-1) drain has a whole dV slot before dP^T(i) reuses its columns.
+// Two independent MMA issue streams, one warp each, interleaved by the tensor pipe:
+//   stream X (owns the ST columns):   S^T(0) ; for each tile i:  [P(i) ready] dV(i) . S^T(i+1)
+//   stream Y (owns the DPT columns):  for each tile i:  [dQ(i-1) drained] dP^T(i) ; [dS(i) ready] dK(i) . dQ(i)
+// so neither chain waits for the other's softmax phase (a single in-order issuer made dP^T(i) queue behind dV(i)).
 //
 // Warps: 0-3 / 4-7 compute warpgroups (thread = kv row; WG0 takes query columns 0-63, WG1 64-127),
 //        8-11 dQ drain warpgroup (TMEM -> swizzled smem -> TMA reduce-add, thread = query row),
-//        12 TMA producer, 13 MMA issuer.
+//        12 TMA producer, 13 MMA stream X, 14 MMA stream Y.
 #include "ptx.cuh"
 #include "fa_host.cuh"
 
@@ -31,7 +32,7 @@ struct BwdParams {
   float scale_log2, scale;
 };
 
-constexpr int kBwdThreads = 448;
+constexpr int kBwdThreads = 480;  // 15 warps (16 x 128 registers does not launch: the register file has no slack)
 constexpr int kT = 128;  // tile edge (query rows and kv rows)
 
 template <int D>
@@ -96,7 +97,11 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
       __trap();
     }
     for (int b = 0; b < kBarCount; ++b) {
-      const uint32_t count = (b == kBarPReady || b == kBarDSReady) ? 256u : (b == kBarDQDrained ? 128u : 1u);
+      uint32_t count = 1u;
+      if (b == kBarPReady || b == kBarDSReady) count = 256u;
+      if (b == kBarDQDrained) count = 128u;
+      // operands shared by both MMA streams are released by two commits
+      if (b == kBarQEmpty0 || b == kBarQEmpty1 || b == kBarDOEmpty || b == kBarDKVDone) count = 2u;
       mbar_init(&bars[b], count);
     }
     fence_mbar_init();
@@ -141,9 +146,9 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
       }
     }
     __syncwarp();
-  } else if (warp == 13) {
-    // ===================================== MMA issuer =====================================
-    if (n_iter > 0) {  // whole warp runs the loop (uniform control flow); one elected lane issues
+  } else if (warp == 13 || warp == 14) {
+    // ===================================== MMA issuers (uniform control flow, one elected lane) ==================
+    if (n_iter > 0) {
       constexpr uint32_t idesc_s = umma_idesc(kBF16, kT, kT, false, false);
       constexpr uint32_t idesc_acc = umma_idesc(kBF16, kT, D, false, true);
       constexpr uint32_t idesc_dq = umma_idesc(kBF16, kT, D, true, true);
@@ -180,53 +185,68 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
       };
 
       mbar_wait(&bars[kBarKV], 0);
-      mbar_wait(&bars[kBarQFull0], 0);
-      tc_fence_after();
-      if (elect_one()) {
-        mma_kmajor(kColST, k_km, q_km);
-        tc_commit(&bars[kBarSFull]);
-      }
-      __syncwarp();
-
-      for (int it = 0; it < n_iter; ++it) {
-        const uint32_t st = it & 1;
-        // ---- dV(it) += P^T dO ; dP^T(it) = V dO^T
-        mbar_wait(&bars[kBarDOFull], it & 1);
-        mbar_wait(&bars[kBarPReady], it & 1);
-        if (it > 0) mbar_wait(&bars[kBarDQDrained], (it - 1) & 1);  // dP^T reuses the dQ(it-1) columns
+      if (warp == 13) {
+        // ---------------- stream X: S^T and dV ----------------
+        mbar_wait(&bars[kBarQFull0], 0);
         tc_fence_after();
+        // Q(it) is read by S^T(it) [X] and dK(it) [Y]: each stream releases it once its own reader is issued.
         if (elect_one()) {
-          mma_from_tmem(kColDV, kColST, do_mn, it > 0);
-          mma_kmajor(kColDPT, v_km, do_km);
-          tc_commit(&bars[kBarDPFull]);
-          tc_commit(&bars[kBarDOEmpty]);
+          mma_kmajor(kColST, k_km, q_km);
+          tc_commit(&bars[kBarSFull]);
+          tc_commit(&bars[kBarQEmpty0]);
         }
         __syncwarp();
-        // ---- S^T(it+1) = K Q^T  (P^T(it) in the S columns has been consumed by dV(it): in-order tensor pipe)
-        if (it + 1 < n_iter) {
-          mbar_wait(&bars[kBarQFull0 + (st ^ 1)], ((it + 1) >> 1) & 1);
+        for (int it = 0; it < n_iter; ++it) {
+          const uint32_t st = it & 1;
+          mbar_wait(&bars[kBarDOFull], it & 1);
+          mbar_wait(&bars[kBarPReady], it & 1);
           tc_fence_after();
           if (elect_one()) {
-            mma_kmajor(kColST, k_km, q_km + (st ^ 1) * kTileLo);
-            tc_commit(&bars[kBarSFull]);
+            mma_from_tmem(kColDV, kColST, do_mn, it > 0);  // dV(it) += P^T dO
+            tc_commit(&bars[kBarDOEmpty]);
+          }
+          __syncwarp();
+          if (it + 1 < n_iter) {
+            mbar_wait(&bars[kBarQFull0 + (st ^ 1)], ((it + 1) >> 1) & 1);
+            tc_fence_after();
+            if (elect_one()) {
+              // S^T(it+1): P^T(it) in the same columns has been consumed by dV(it) (in-order within this stream)
+              mma_kmajor(kColST, k_km, q_km + (st ^ 1) * kTileLo);
+              tc_commit(&bars[kBarSFull]);
+              tc_commit(&bars[kBarQEmpty0 + (st ^ 1)]);
+            }
+            __syncwarp();
+          }
+        }
+      } else {
+        // ---------------- stream Y: dP^T, dK, dQ ----------------
+        for (int it = 0; it < n_iter; ++it) {
+          const uint32_t st = it & 1;
+          mbar_wait(&bars[kBarDOFull], it & 1);
+          if (it > 0) mbar_wait(&bars[kBarDQDrained], (it - 1) & 1);  // dP^T reuses the dQ(it-1) columns
+          tc_fence_after();
+          if (elect_one()) {
+            mma_kmajor(kColDPT, v_km, do_km);  // dP^T(it) = V dO^T
+            tc_commit(&bars[kBarDPFull]);
+            tc_commit(&bars[kBarDOEmpty]);
+          }
+          __syncwarp();
+          mbar_wait(&bars[kBarQFull0 + st], (it >> 1) & 1);
+          mbar_wait(&bars[kBarDSReady], it & 1);
+          tc_fence_after();
+          if (elect_one()) {
+            mma_from_tmem(kColDK, kColDPT, q_mn + st * kTileLo, it > 0);  // dK(it) += dS^T Q
+            tc_commit(&bars[kBarQEmpty0 + st]);
+            mma_dq();                                                      // dQ(it) = dS K
+            tc_commit(&bars[kBarDQFull]);
           }
           __syncwarp();
         }
-        // ---- dK(it) += dS^T Q ; dQ(it) = dS K
-        mbar_wait(&bars[kBarDSReady], it & 1);
-        tc_fence_after();
-        if (elect_one()) {
-          mma_from_tmem(kColDK, kColDPT, q_mn + st * kTileLo, it > 0);
-          tc_commit(&bars[kBarQEmpty0 + st]);
-          mma_dq();
-          tc_commit(&bars[kBarDQFull]);
-        }
-        __syncwarp();
       }
       tc_commit_elect(&bars[kBarDKVDone]);
     }
     __syncwarp();
-  } else if (warp >= 8) {
+  } else if (warp >= 8 && warp < 12) {
     // ===================================== dQ drain warpgroup =====================================
     const int row = threadIdx.x - 256;  // query row inside the tile == TMEM lane
     const uint32_t lane_sel = static_cast<uint32_t>((warp & 3) * 32) << 16;
@@ -260,7 +280,7 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
       }
     }
     if (row == 0) tma_store_wait_all<0>();
-  } else {
+  } else if (warp < 8) {
     // ===================================== compute warpgroups =====================================
     const int wg = warp >> 2;
     const int r = threadIdx.x & 127;  // kv row inside the tile == TMEM lane
