@@ -41,6 +41,7 @@ WORKLOADS = {
     "c2": (4, 16, 4096, 128, True),        # BASELINE configs[1]
     "headline": (4, 16, 8192, 128, True),  # north-star "bf16 d=128 N=8K causal"
     "c4": (32, 32, 8192, 128, True),       # BASELINE configs[3]: TOTAL shape, batch*head split over the ranks
+    "c5": (1, 16, 131072, 128, True),      # BASELINE configs[4]: TOTAL shape, sequence split over the ranks (ring)
 }
 NOMINAL_BF16_TFLOPS = 2250.0
 FALLBACK_BF16_TFLOPS = 1590.0
@@ -356,6 +357,77 @@ def run_ours(args, workload, name):
         dist.destroy_process_group()
 
 
+def run_ring(args, workload, name):
+    """BASELINE C5: long-context causal ring attention, sequence zig-zag-sharded over the ranks, NCCL send/recv of the
+    K/V (and dK/dV) blocks overlapped with compute, partial outputs merged by LSE in the kernel epilogue."""
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", "29531")
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    from dist.ring import ring_attention
+
+    b, h, n, d, causal = workload
+    if n % (2 * world * 128):
+        raise SystemExit("c5: N must be a multiple of 256 * n_gpus")
+    n_local = n // world
+    f_fwd, f_bwd = flops(b, h, n, d, causal)
+    g = torch.Generator(device=dev).manual_seed(rank)
+    q, k, v = (torch.randn((b * h, n_local, d), generator=g, device=dev, dtype=torch.bfloat16).requires_grad_(True)
+               for _ in range(3))
+    do = torch.randn((b * h, n_local, d), generator=g, device=dev, dtype=torch.bfloat16)
+    scale = d ** -0.5
+
+    def step():
+        o, lse = ring_attention(q, k, v, causal=causal, softmax_scale=scale)
+        torch.autograd.backward(o, do)
+        q.grad = k.grad = v.grad = None
+
+    def barrier():
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t0 = time.time()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    t1 = time.time()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / args.steps
+    clocks = sampler.stop(t0, t1) if rank == 0 else None
+    value = (f_fwd + f_bwd) / (ms_step * 1e-3) / 1e12
+    if rank == 0:
+        peaks = measured_peaks()
+        kv_bytes = 2 * b * h * n_local * d * 2
+        print(json.dumps({
+            "metric": "attention fwd+bwd TFLOP/s", "value": value, "unit": "TFLOP/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": name, "B": b, "H": h, "N_total": n, "N_per_gpu": n_local, "d": d, "causal": causal,
+                       "parallelism": f"ring attention x{world} (zig-zag sequence shards, NCCL P2P)",
+                       "nvlink_bytes_per_gpu_per_step": (world - 1) * kv_bytes + world * (kv_bytes + 2 * kv_bytes)},
+            "frac_of_nominal_bf16_peak": value / world / NOMINAL_BF16_TFLOPS,
+            "frac_of_measured_bf16_peak": value / world / peaks["burst"],
+            "clocks": clocks, "gpu_launches": None}), flush=True)
+    dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -378,6 +450,9 @@ def main():
                "--gpus", str(args.gpus), "--steps", str(args.steps), "--warmup", str(args.warmup),
                "--workload", args.workload]
         raise SystemExit(subprocess.call(cmd))
+    if args.workload == "c5":
+        run_ring(args, workload, args.workload)
+        return
     run_ours(args, workload, args.workload)
 
 

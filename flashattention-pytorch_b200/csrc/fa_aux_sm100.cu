@@ -39,7 +39,7 @@ __global__ void __launch_bounds__(256) fa_dq_finish_kernel(const float* __restri
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
   for (long long v = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; v < total; v += stride) {
     const long long b = v / per_slice_vec, e = (v % per_slice_vec) * 8;
-    const float* src = acc + b * slice_elems + e;  // the accumulator is always dense
+    const float* src = acc + b * q_bh_stride + e;  // the accumulator shares q's slice stride
     const float4 x = *reinterpret_cast<const float4*>(src);
     const float4 y = *reinterpret_cast<const float4*>(src + 4);
     uint4 w;

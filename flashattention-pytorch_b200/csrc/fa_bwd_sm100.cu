@@ -474,7 +474,7 @@ static int launch_bwd(const Geometry& g, const void* q, const void* k, const voi
   if ((rc = make_tmap_3d(&tm_v, v, elem, D, g.n_kv, g.bh, g.kv_bh_stride, 64, kT))) return rc;
   if ((rc = make_tmap_3d(&tm_dk, dk, elem, D, g.n_kv, g.bh, g.kv_bh_stride, 64, kT))) return rc;
   if ((rc = make_tmap_3d(&tm_dv, dv, elem, D, g.n_kv, g.bh, g.kv_bh_stride, 64, kT))) return rc;
-  if ((rc = make_tmap_3d(&tm_dq, dq_accum, kElemF32, D, g.n_q, g.bh, g.n_q * D, 32, kT))) return rc;
+  if ((rc = make_tmap_3d(&tm_dq, dq_accum, kElemF32, D, g.n_q, g.bh, g.q_bh_stride, 32, kT))) return rc;
 
   BwdParams p;
   p.rowstats = rowstats;

@@ -1,0 +1,295 @@
+"""Ring attention over a sequence-sharded context (BASELINE config C5).
+
+The reference has no distributed code; the exchange pattern is derived from its online-softmax update
+(reference ``src/fa1/torch/impl.py:53-62``): attention over a union of key blocks is the log-sum-exp merge of the
+per-block partials.  One process per GPU; K/V blocks (and, in the backward, their fp32 dK/dV accumulators) travel
+around the ring with NCCL send/recv while the current block is being processed.
+
+Layout (causal): the sequence is cut into 2P chunks of c rows; rank r owns chunks r and 2P-1-r ("zig-zag"), stored
+as one local tensor (bh, 2c, d) = [chunk r | chunk 2P-1-r].  Every ring step is then exactly one kernel launch of equal
+cost on every rank:
+
+    source rank p == r :  chunk_a x K_a causal,  then chunk_b x [K_a | K_b] causal with q_row0 = c
+    p <  r             :  [chunk_a | chunk_b] x K_a          (all visible, non-causal call)
+    p >  r             :  chunk_b x [K_a | K_b]              (all visible, non-causal call)
+
+(the local [K_a | K_b] tensor behaves like a contiguous sequence for chunk_b because every key of K_a precedes it and
+K_b is its own diagonal block).  Partials are merged inside the forward kernel's epilogue (``merge=True``).
+Non-causal attention needs no zig-zag: every step is [all local q] x [visiting block].
+
+The schedule is written once as a generator that yields its communication requests, so the same code runs
+  * under ``torch.distributed`` (``TorchRingDriver``: batched isend/irecv, overlapped with compute), and
+  * inside ONE process for all P ranks (``run_loopback``) — used by the single-GPU and CPU tests.
+The block operator is injected (``BlockOps``); the product default is the sm_100a library.  Tests may inject a CPU
+implementation — nothing in this module imports the oracle.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Callable, Generator, List, Optional, Sequence, Tuple
+
+import torch
+
+# ----------------------------------------------------------------------------------------------------------------------
+# zig-zag partition helpers
+# ----------------------------------------------------------------------------------------------------------------------
+
+
+def zigzag_chunk_ids(rank: int, world: int) -> Tuple[int, int]:
+    return rank, 2 * world - 1 - rank
+
+
+def zigzag_split(x: torch.Tensor, world: int, dim: int = -2) -> List[torch.Tensor]:
+    """Global tensor -> per-rank local tensors [chunk r | chunk 2P-1-r] along ``dim``."""
+    n = x.shape[dim]
+    if n % (2 * world):
+        raise ValueError(f"sequence length {n} must be a multiple of 2*world = {2 * world}")
+    chunks = x.chunk(2 * world, dim=dim)
+    return [torch.cat([chunks[a], chunks[b]], dim=dim).contiguous()
+            for a, b in (zigzag_chunk_ids(r, world) for r in range(world))]
+
+
+def zigzag_merge(parts: Sequence[torch.Tensor], dim: int = -2) -> torch.Tensor:
+    """Inverse of ``zigzag_split``."""
+    world = len(parts)
+    chunks: List[Optional[torch.Tensor]] = [None] * (2 * world)
+    for r, p in enumerate(parts):
+        a, b = p.chunk(2, dim=dim)
+        ia, ib = zigzag_chunk_ids(r, world)
+        chunks[ia], chunks[ib] = a, b
+    return torch.cat(chunks, dim=dim)
+
+
+def contiguous_split(x: torch.Tensor, world: int, dim: int = -2) -> List[torch.Tensor]:
+    return [c.contiguous() for c in x.chunk(world, dim=dim)]
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# block operator
+# ----------------------------------------------------------------------------------------------------------------------
+@dataclass
+class BlockOps:
+    """The single-device attention primitives the ring is built from (signatures of the shim's raw entry points)."""
+
+    fwd: Callable      # (q, k, v, causal, scale, *, q_row0, kv_col0, out, lse, merge) -> (out, lse)
+    prepare: Callable  # (o, do, lse) -> rowstats
+    bwd: Callable      # (q, k, v, o, do, lse, causal, scale, *, q_row0, kv_col0, rowstats, dq_accum) -> (None, dk, dv)
+    finish: Callable   # (dq_accum, dtype, scale) -> dq
+
+
+def cuda_block_ops() -> BlockOps:
+    """The product operator: hand-written sm_100a kernels through the C ABI.  Raises if the library is missing."""
+    import flashattention_lab_cuda as ext
+
+    ext.load_library()
+    return BlockOps(fwd=ext.fwd_raw, prepare=ext.bwd_prepare_raw, bwd=ext.bwd_raw, finish=ext.dq_finish_raw)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# the schedule (generators: ``tag, payload = yield``-style coroutines driven by a communicator)
+# ----------------------------------------------------------------------------------------------------------------------
+# yield ("post", [tensors to send to rank+1])  -> handle        (receive buffers come from rank-1)
+# yield ("wait", handle)                       -> [tensors received from rank-1]
+Coroutine = Generator[tuple, object, tuple]
+
+
+def ring_forward(ops: BlockOps, rank: int, world: int, q, k, v, causal: bool, scale: float) -> Coroutine:
+    """q, k, v: local (bh, n_local, d).  Returns (o, lse) for the local rows."""
+    bh, n_local, d = q.shape
+    c = n_local // 2
+    o = torch.empty_like(q)
+    lse = torch.empty((bh, n_local), device=q.device, dtype=torch.float32)
+    kv = [k, v]
+    for step in range(world):
+        handle = None
+        if step + 1 < world:
+            handle = yield ("post", kv)  # next block starts moving before this one is consumed
+        src = (rank - step) % world
+        kb, vb = kv
+        if not causal:
+            ops.fwd(q, kb, vb, False, scale, out=o, lse=lse, merge=step > 0)
+        elif src == rank:
+            ops.fwd(q[:, :c], kb[:, :c], vb[:, :c], True, scale, out=o[:, :c], lse=lse[:, :c], merge=False)
+            ops.fwd(q[:, c:], kb, vb, True, scale, q_row0=c, kv_col0=0, out=o[:, c:], lse=lse[:, c:], merge=False)
+        elif src < rank:
+            ops.fwd(q, kb[:, :c], vb[:, :c], False, scale, out=o, lse=lse, merge=True)
+        else:
+            ops.fwd(q[:, c:], kb, vb, False, scale, out=o[:, c:], lse=lse[:, c:], merge=True)
+        if handle is not None:
+            kv = yield ("wait", handle)
+    return o, lse
+
+
+def ring_backward(ops: BlockOps, rank: int, world: int, q, k, v, o, lse, do, causal: bool, scale: float) -> Coroutine:
+    """Returns (dq, dk, dv) for the local rows.  dQ accumulates locally in fp32; each K/V block travels with its fp32
+    dK/dV accumulators and is home again, complete, after ``world`` hops."""
+    bh, n_local, d = q.shape
+    c = n_local // 2
+    dq_acc = torch.zeros(q.shape, device=q.device, dtype=torch.float32)
+    stats_all = ops.prepare(o, do, lse)
+    stats_a = stats_b = None
+    if causal:
+        stats_a = ops.prepare(o[:, :c], do[:, :c], lse[:, :c])
+        stats_b = ops.prepare(o[:, c:], do[:, c:], lse[:, c:])
+    kv = [k, v]
+    acc = [torch.zeros(k.shape, device=k.device, dtype=torch.float32),
+           torch.zeros(v.shape, device=v.device, dtype=torch.float32)]
+    acc_handle = None
+    for step in range(world):
+        kv_handle = None
+        if step + 1 < world:
+            kv_handle = yield ("post", kv)
+        src = (rank - step) % world
+        kb, vb = kv
+        # partial dK/dV of the visiting block: list of (row slice, dk, dv)
+        parts = []
+        if not causal:
+            _, dk, dv = ops.bwd(q, kb, vb, None, do, None, False, scale, rowstats=stats_all, dq_accum=dq_acc)
+            parts.append((slice(None), dk, dv))
+        elif src == rank:
+            _, dk, dv = ops.bwd(q[:, :c], kb[:, :c], vb[:, :c], None, do[:, :c], None, True, scale,
+                                rowstats=stats_a, dq_accum=dq_acc[:, :c])
+            parts.append((slice(0, c), dk, dv))
+            _, dk, dv = ops.bwd(q[:, c:], kb, vb, None, do[:, c:], None, True, scale, q_row0=c, kv_col0=0,
+                                rowstats=stats_b, dq_accum=dq_acc[:, c:])
+            parts.append((slice(None), dk, dv))
+        elif src < rank:
+            _, dk, dv = ops.bwd(q, kb[:, :c], vb[:, :c], None, do, None, False, scale, rowstats=stats_all,
+                                dq_accum=dq_acc)
+            parts.append((slice(0, c), dk, dv))
+        else:
+            _, dk, dv = ops.bwd(q[:, c:], kb, vb, None, do[:, c:], None, False, scale, rowstats=stats_b,
+                                dq_accum=dq_acc[:, c:])
+            parts.append((slice(None), dk, dv))
+        if acc_handle is not None:  # accumulators of the block we are working on arrive from the previous rank
+            acc = yield ("wait", acc_handle)
+        for rows, dk, dv in parts:
+            acc[0][:, rows] += dk
+            acc[1][:, rows] += dv
+        acc_handle = yield ("post", acc)  # they move on with their block (the last hop brings ours home)
+        if kv_handle is not None:
+            kv = yield ("wait", kv_handle)
+    acc = yield ("wait", acc_handle)
+    dq = ops.finish(dq_acc, q.dtype, scale)
+    return dq, acc[0].to(k.dtype), acc[1].to(v.dtype)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# drivers
+# ----------------------------------------------------------------------------------------------------------------------
+def run_loopback(coroutines: Sequence[Coroutine]) -> List[tuple]:
+    """Run the P per-rank coroutines of one collective call inside one process (ranks execute in lock-step between
+    communication points; sends are delivered to rank+1 by reference)."""
+    world = len(coroutines)
+    results: List[Optional[tuple]] = [None] * world
+    mailbox = [dict() for _ in range(world)]  # mailbox[r][seq] = tensors posted by rank r
+    seq = [0] * world
+    pending = [None] * world  # value to send into each coroutine next
+    live = list(range(world))
+    # advance every coroutine to its first yield
+    requests = {}
+    for r in live:
+        try:
+            requests[r] = next(coroutines[r])
+        except StopIteration as stop:
+            results[r] = stop.value
+    while requests:
+        progressed = False
+        for r in sorted(requests):
+            kind, payload = requests[r]
+            if kind == "post":
+                mailbox[r][seq[r]] = [t for t in payload]
+                reply = (r, seq[r])
+                seq[r] += 1
+            else:  # wait on a handle (owner rank, seq): data comes from rank-1's post with the same sequence number
+                _, s = payload
+                src = (r - 1) % world
+                if s not in mailbox[src]:
+                    continue  # neighbour has not posted yet: let the others run
+                reply = [t.clone() for t in mailbox[src].pop(s)]
+            progressed = True
+            try:
+                requests[r] = coroutines[r].send(reply)
+            except StopIteration as stop:
+                results[r] = stop.value
+                del requests[r]
+        if not progressed:
+            raise RuntimeError("ring loopback deadlock: every rank is waiting")
+    return results  # type: ignore[return-value]
+
+
+class TorchRingDriver:
+    """Drives one rank's coroutine with torch.distributed point-to-point ops (NCCL on GPUs, gloo on CPU)."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+
+        self.dist = dist
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        self.next_rank = dist.get_global_rank(group, (self.rank + 1) % self.world) if group else (self.rank + 1) % self.world
+        self.prev_rank = dist.get_global_rank(group, (self.rank - 1) % self.world) if group else (self.rank - 1) % self.world
+
+    def _post(self, tensors):
+        dist = self.dist
+        sends = [t.contiguous() for t in tensors]
+        recvs = [torch.empty_like(t) for t in sends]
+        ops = []
+        for s, r in zip(sends, recvs):
+            ops.append(dist.P2POp(dist.isend, s, self.next_rank, self.group))
+            ops.append(dist.P2POp(dist.irecv, r, self.prev_rank, self.group))
+        reqs = dist.batch_isend_irecv(ops)
+        return reqs, recvs, sends  # keep `sends` alive until the wait
+
+    def run(self, coroutine: Coroutine) -> tuple:
+        try:
+            request = next(coroutine)
+            while True:
+                kind, payload = request
+                if kind == "post":
+                    reply = self._post(payload)
+                else:
+                    reqs, recvs, _sends = payload
+                    for rq in reqs:
+                        rq.wait()
+                    reply = recvs
+                request = coroutine.send(reply)
+        except StopIteration as stop:
+            return stop.value
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# public API
+# ----------------------------------------------------------------------------------------------------------------------
+class _RingAttnFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, q, k, v, causal, softmax_scale, group, ops):
+        driver = TorchRingDriver(group)
+        ops = ops or cuda_block_ops()
+        q, k, v = q.contiguous(), k.contiguous(), v.contiguous()
+        o, lse = driver.run(ring_forward(ops, driver.rank, driver.world, q, k, v, bool(causal), float(softmax_scale)))
+        ctx.save_for_backward(q, k, v, o, lse)
+        ctx.meta = (bool(causal), float(softmax_scale), group, ops)
+        return o, lse
+
+    @staticmethod
+    def backward(ctx, do, dlse):
+        q, k, v, o, lse = ctx.saved_tensors
+        causal, scale, group, ops = ctx.meta
+        driver = TorchRingDriver(group)
+        dq, dk, dv = driver.run(ring_backward(ops, driver.rank, driver.world, q, k, v, o, lse, do.contiguous(), causal,
+                                              scale))
+        return dq, dk, dv, None, None, None, None
+
+
+def ring_attention(q, k, v, causal=False, softmax_scale=None, group=None, ops: Optional[BlockOps] = None):
+    """Sequence-parallel attention.  q, k, v: this rank's LOCAL rows, (bh, n_local, d) or (B, H, n_local, d), head dim
+    64 or 128; for ``causal=True`` they must be laid out zig-zag (``zigzag_split``).  Returns (o, lse) for the local
+    rows; differentiable."""
+    if softmax_scale is None:
+        softmax_scale = q.shape[-1] ** -0.5
+    lead = q.shape[:-2]
+    qb, kb, vb = (t.reshape(-1, t.shape[-2], t.shape[-1]) for t in (q, k, v))
+    o, lse = _RingAttnFn.apply(qb, kb, vb, causal, softmax_scale, group, ops)
+    return o.reshape(*lead, *o.shape[-2:]), lse.reshape(*lead, lse.shape[-1])

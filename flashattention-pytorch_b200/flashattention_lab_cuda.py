@@ -152,10 +152,33 @@ def make_shape(bh, n_q, n_kv, d, dtype_code, causal, softmax_scale, q_row0=0, kv
 
 
 # ------------------------------------------------------------------------------------------------------------------
-# raw (already padded / contiguous) entry points — also used by the sharding and ring-attention drivers
+# raw entry points (head dim already 64/128) — also used by the sharding and ring-attention drivers.
+# Tensors may be views of a larger (bh, n, d) tensor along n: rows must be dense, the slice stride is free.
 # ------------------------------------------------------------------------------------------------------------------
+def _slice_stride(t: torch.Tensor) -> int:
+    if t.dim() == 3:
+        if t.stride(2) != 1 or t.stride(1) != t.shape[2]:
+            raise RuntimeError("rows must be dense (stride(1) == head_dim, stride(2) == 1)")
+    elif t.dim() == 2:
+        if t.stride(1) != 1:
+            raise RuntimeError("lse rows must be dense")
+    return t.stride(0) if t.shape[0] > 1 else (t.shape[1] * (t.shape[2] if t.dim() == 3 else 1))
+
+
+def _same_stride(ref: torch.Tensor, *others: torch.Tensor) -> int:
+    st = _slice_stride(ref)
+    for o in others:
+        if o.shape[0] > 1 and _slice_stride(o) != st:
+            raise RuntimeError("tensors that share a geometry must share their slice stride")
+    return st
+
+
+def _empty_like_strided(t: torch.Tensor, dtype=None) -> torch.Tensor:
+    return torch.empty_strided(t.shape, t.stride(), dtype=dtype or t.dtype, device=t.device)
+
+
 def fwd_raw(q, k, v, causal, softmax_scale, *, q_row0=0, kv_col0=0, out=None, lse=None, merge=False):
-    """q: (bh, n_q, d), k/v: (bh, n_kv, d), d in {64,128}, contiguous.  Returns (o, lse).
+    """q: (bh, n_q, d), k/v: (bh, n_kv, d), d in {64,128}.  Returns (o, lse).
 
     ``merge=True`` folds the new partial into the given ``out``/``lse`` by log-sum-exp (ring attention)."""
     lib = load_library()
@@ -164,9 +187,10 @@ def fwd_raw(q, k, v, causal, softmax_scale, *, q_row0=0, kv_col0=0, out=None, ls
     if out is None:
         if merge:
             raise ValueError("merge=True needs out/lse from the previous step")
-        out = torch.empty_like(q)
+        out = _empty_like_strided(q)
         lse = torch.empty((bh, n_q), device=q.device, dtype=torch.float32)
-    shape = make_shape(bh, n_q, n_kv, d, _dtype_code(q), causal, softmax_scale, q_row0, kv_col0)
+    shape = make_shape(bh, n_q, n_kv, d, _dtype_code(q), causal, softmax_scale, q_row0, kv_col0,
+                       _same_stride(q, out), _same_stride(k, v), _slice_stride(lse))
     prev_o = out.data_ptr() if merge else None
     prev_lse = lse.data_ptr() if merge else None
     with torch.cuda.device(q.device):
@@ -177,10 +201,10 @@ def fwd_raw(q, k, v, causal, softmax_scale, *, q_row0=0, kv_col0=0, out=None, ls
 
 
 def bwd_prepare_raw(o, do, lse):
-    """Pre-pass of the backward: packs (lse * log2e, delta = rowsum(dO o O)) per 128-row query tile."""
+    """Pre-pass of the backward: packs (-lse * log2e, -delta = -rowsum(dO o O)) per 128-row query tile."""
     lib = load_library()
     bh, n_q, d = o.shape
-    shape = make_shape(bh, n_q, n_q, d, _dtype_code(o), False, 1.0)
+    shape = make_shape(bh, n_q, n_q, d, _dtype_code(o), False, 1.0, 0, 0, _same_stride(o, do), 0, _slice_stride(lse))
     rowstats = torch.empty(lib.fa_sm100_rowstats_bytes(ctypes.byref(shape)) // 4, device=o.device,
                            dtype=torch.float32)
     with torch.cuda.device(o.device):
@@ -190,28 +214,30 @@ def bwd_prepare_raw(o, do, lse):
 
 
 def bwd_raw(q, k, v, o, do, lse, causal, softmax_scale, *, q_row0=0, kv_col0=0, rowstats=None, dq_accum=None):
-    """Backward on padded/contiguous tensors (d in {64,128}).
+    """Backward (d in {64,128}).
 
     Plain call: returns (dq, dk, dv) in the input dtype.
-    Ring call (``dq_accum`` fp32 (bh,n_q,d) given, ``rowstats`` from ``bwd_prepare_raw``): dQ partials are added into
-    ``dq_accum`` (the caller finishes with ``dq_finish_raw`` after the last step) and (None, dk, dv) of THIS K/V
-    block is returned."""
+    Ring call (``dq_accum`` fp32 with q's shape AND strides given, ``rowstats`` from ``bwd_prepare_raw``): dQ partials
+    are added into ``dq_accum`` (finish with ``dq_finish_raw`` after the last step); returns (None, dk, dv) of THIS
+    K/V block (``o``/``lse`` may then be None)."""
     lib = load_library()
     bh, n_q, d = q.shape
     n_kv = k.shape[1]
-    shape = make_shape(bh, n_q, n_kv, d, _dtype_code(q), causal, softmax_scale, q_row0, kv_col0)
-    sp = ctypes.byref(shape)
-    stream = _stream_ptr(q)
     if rowstats is None:
         rowstats = bwd_prepare_raw(o, do, lse)
     ring = dq_accum is not None
     if not ring:
-        dq_accum = torch.zeros((bh, n_q, d), device=q.device, dtype=torch.float32)
-    dk = torch.empty_like(k)
-    dv = torch.empty_like(v)
+        dq_accum = torch.zeros(q.shape, device=q.device, dtype=torch.float32)
+        if bh > 1 and _slice_stride(q) != n_q * d:
+            q, do = q.contiguous(), do.contiguous()
+    dk = _empty_like_strided(k)
+    dv = _empty_like_strided(k)
+    shape = make_shape(bh, n_q, n_kv, d, _dtype_code(q), causal, softmax_scale, q_row0, kv_col0,
+                       _same_stride(q, do, dq_accum), _same_stride(k, v, dk, dv), 0)
     with torch.cuda.device(q.device):
-        _check(lib.fa_sm100_bwd(sp, q.data_ptr(), k.data_ptr(), v.data_ptr(), do.data_ptr(), rowstats.data_ptr(),
-                                dq_accum.data_ptr(), dk.data_ptr(), dv.data_ptr(), stream), "fa_sm100_bwd")
+        _check(lib.fa_sm100_bwd(ctypes.byref(shape), q.data_ptr(), k.data_ptr(), v.data_ptr(), do.data_ptr(),
+                                rowstats.data_ptr(), dq_accum.data_ptr(), dk.data_ptr(), dv.data_ptr(),
+                                _stream_ptr(q)), "fa_sm100_bwd")
     if ring:
         return None, dk, dv
     return dq_finish_raw(dq_accum, q.dtype, softmax_scale), dk, dv
@@ -220,8 +246,8 @@ def bwd_raw(q, k, v, o, do, lse, causal, softmax_scale, *, q_row0=0, kv_col0=0, 
 def dq_finish_raw(dq_accum, dtype, softmax_scale):
     lib = load_library()
     bh, n_q, d = dq_accum.shape
-    shape = make_shape(bh, n_q, n_q, d, _DTYPES[dtype], False, softmax_scale)
-    dq = torch.empty((bh, n_q, d), device=dq_accum.device, dtype=dtype)
+    dq = _empty_like_strided(dq_accum, dtype)
+    shape = make_shape(bh, n_q, n_q, d, _DTYPES[dtype], False, softmax_scale, 0, 0, _same_stride(dq_accum, dq))
     with torch.cuda.device(dq_accum.device):
         _check(lib.fa_sm100_dq_finish(ctypes.byref(shape), dq_accum.data_ptr(), dq.data_ptr(),
                                       _stream_ptr(dq_accum)), "fa_sm100_dq_finish")

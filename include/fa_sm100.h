@@ -61,7 +61,8 @@ int fa_sm100_version(void);
 const char* fa_sm100_strerror(int code);
 
 /* Scratch the caller must provide to the backward:
- *   dq_accum : fp32 dQ accumulator, bh * n_q * d elements, ZEROED by the caller before fa_sm100_bwd;
+ *   dq_accum : fp32 dQ accumulator with q's geometry (bh slices of n_q * d, slice stride q_bh_stride), ZEROED by
+ *              the caller before the first fa_sm100_bwd that adds into it;
  *   rowstats : per-query-row statistics packed per 128-row tile, bh * ceil(n_q/128) * 256 floats. */
 size_t fa_sm100_dq_accum_bytes(const fa_sm100_shape* s);
 size_t fa_sm100_rowstats_bytes(const fa_sm100_shape* s);
