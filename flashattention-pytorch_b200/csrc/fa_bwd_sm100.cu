@@ -43,19 +43,23 @@ struct BwdCfg {
   static constexpr int kDqStageBytes = kT * 32 * 4;  // 128 rows x 32 fp32 columns
   static constexpr int kOffK = 0;
   static constexpr int kOffV = kOffK + kTileBytes;
-  static constexpr int kOffQ = kOffV + kTileBytes;       // 2 stages
-  static constexpr int kOffDO = kOffQ + 2 * kTileBytes;  // 1 stage
-  static constexpr int kOffDS = kOffDO + kTileBytes;
-  static constexpr int kOffDQ = kOffDS + kDsBytes;        // 2 staging buffers
-  static constexpr int kOffStats = kOffDQ + 2 * kDqStageBytes;  // 2 stages x 1 KiB
+  static constexpr int kOffQ = kOffV + kTileBytes;        // 2 stages
+  static constexpr int kOffDO = kOffQ + 2 * kTileBytes;   // 2 stages
+  static constexpr int kOffDS = kOffDO + 2 * kTileBytes;  // dS^T tile
+  // dQ staging (2 x 16 KiB): at D = 128 there is no room left, so it borrows the (dead) dO stage of the tile being
+  // drained; at D = 64 it has its own buffers
+  static constexpr bool kStageInDO = (D == 128);
+  static constexpr int kOffStage = kOffDS + kDsBytes;
+  static constexpr int kOffStats = kOffStage + (kStageInDO ? 0 : 2 * kDqStageBytes);  // 2 stages x 1 KiB
   static constexpr int kOffBars = kOffStats + 2 * 1024;
   static constexpr int kSmemBytes = kOffBars + 256;
 };
 static_assert(BwdCfg<128>::kSmemBytes <= 232448, "backward smem budget");
 
 enum BwdBar : int {
-  kBarKV = 0, kBarQFull0, kBarQFull1, kBarQEmpty0, kBarQEmpty1, kBarDOFull, kBarDOEmpty, kBarSFull, kBarDPFull,
-  kBarPReady, kBarDSReady, kBarDQFull, kBarDQDrained, kBarDKVDone, kBarCount
+  kBarKV = 0, kBarQFull0, kBarQFull1, kBarQEmpty0, kBarQEmpty1, kBarDOFull0, kBarDOFull1, kBarDOEmpty0, kBarDOEmpty1,
+  kBarSFull, kBarDPFull, kBarPReady, kBarDSReady, kBarDQFull, kBarDQDrained, kBarStageFree0, kBarStageFree1,
+  kBarDKVDone, kBarCount
 };
 
 template <int D, bool kBF16>
@@ -74,7 +78,6 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
   uint8_t* q_smem = smem + Cfg::kOffQ;
   uint8_t* do_smem = smem + Cfg::kOffDO;
   uint8_t* ds_smem = smem + Cfg::kOffDS;
-  uint8_t* dq_smem = smem + Cfg::kOffDQ;
   float* stats_smem = reinterpret_cast<float*>(smem + Cfg::kOffStats);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kOffBars);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kBarCount);
@@ -101,7 +104,8 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
       if (b == kBarPReady || b == kBarDSReady) count = 256u;
       if (b == kBarDQDrained) count = 128u;
       // operands shared by both MMA streams are released by two commits
-      if (b == kBarQEmpty0 || b == kBarQEmpty1 || b == kBarDOEmpty || b == kBarDKVDone) count = 2u;
+      if (b == kBarQEmpty0 || b == kBarQEmpty1 || b == kBarDOEmpty0 || b == kBarDOEmpty1 || b == kBarDKVDone)
+        count = 2u;
       mbar_init(&bars[b], count);
     }
     fence_mbar_init();
@@ -139,10 +143,12 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
           tma_load_3d(q_smem + st * Cfg::kTileBytes + c * kSub, &tm_q, &bars[kBarQFull0 + st], c * 64, i * kT, bh);
         bulk_load_1d(stats_smem + st * 256, p.rowstats + (static_cast<long long>(bh) * p.nqt + i) * 256, 1024,
                      &bars[kBarQFull0 + st]);
-        mbar_wait(&bars[kBarDOEmpty], (it & 1) ^ 1);
-        mbar_arrive_expect_tx(&bars[kBarDOFull], Cfg::kTileBytes);
+        mbar_wait(&bars[kBarDOEmpty0 + st], ((it >> 1) & 1) ^ 1);     // dV / dP of the previous user are done ...
+        if constexpr (Cfg::kStageInDO)
+          mbar_wait(&bars[kBarStageFree0 + st], ((it >> 1) & 1) ^ 1);  // ... and so is the dQ reduce staged in this buffer
+        mbar_arrive_expect_tx(&bars[kBarDOFull0 + st], Cfg::kTileBytes);
         for (int c = 0; c < kChunks; ++c)
-          tma_load_3d(do_smem + c * kSub, &tm_do, &bars[kBarDOFull], c * 64, i * kT, bh);
+          tma_load_3d(do_smem + st * Cfg::kTileBytes + c * kSub, &tm_do, &bars[kBarDOFull0 + st], c * 64, i * kT, bh);
       }
     }
     __syncwarp();
@@ -198,12 +204,12 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
         __syncwarp();
         for (int it = 0; it < n_iter; ++it) {
           const uint32_t st = it & 1;
-          mbar_wait(&bars[kBarDOFull], it & 1);
+          mbar_wait(&bars[kBarDOFull0 + st], (it >> 1) & 1);
           mbar_wait(&bars[kBarPReady], it & 1);
           tc_fence_after();
           if (elect_one()) {
-            mma_from_tmem(kColDV, kColST, do_mn, it > 0);  // dV(it) += P^T dO
-            tc_commit(&bars[kBarDOEmpty]);
+            mma_from_tmem(kColDV, kColST, do_mn + st * kTileLo, it > 0);  // dV(it) += P^T dO
+            tc_commit(&bars[kBarDOEmpty0 + st]);
           }
           __syncwarp();
           if (it + 1 < n_iter) {
@@ -222,13 +228,13 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
         // ---------------- stream Y: dP^T, dK, dQ ----------------
         for (int it = 0; it < n_iter; ++it) {
           const uint32_t st = it & 1;
-          mbar_wait(&bars[kBarDOFull], it & 1);
+          mbar_wait(&bars[kBarDOFull0 + st], (it >> 1) & 1);
           if (it > 0) mbar_wait(&bars[kBarDQDrained], (it - 1) & 1);  // dP^T reuses the dQ(it-1) columns
           tc_fence_after();
           if (elect_one()) {
-            mma_kmajor(kColDPT, v_km, do_km);  // dP^T(it) = V dO^T
+            mma_kmajor(kColDPT, v_km, do_km + st * kTileLo);  // dP^T(it) = V dO^T
             tc_commit(&bars[kBarDPFull]);
-            tc_commit(&bars[kBarDOEmpty]);
+            tc_commit(&bars[kBarDOEmpty0 + st]);
           }
           __syncwarp();
           mbar_wait(&bars[kBarQFull0 + st], (it >> 1) & 1);
@@ -250,33 +256,54 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
     // ===================================== dQ drain warpgroup =====================================
     const int row = threadIdx.x - 256;  // query row inside the tile == TMEM lane
     const uint32_t lane_sel = static_cast<uint32_t>((warp & 3) * 32) << 16;
+    // dQ(it) sits in the DPT columns.  Two 64-column halves: each is read into registers, written to two 16 KiB
+    // staging buffers (128-byte swizzled rows of 32 fp32) and reduce-added into dq_accum by TMA.  The staging buffers
+    // are the dO stage of this very tile: dO(it) is dead once dV(it) and dP^T(it) have run, and dO(it+2) is not needed
+    // for more than a full iteration, so the slow L2 reduce never sits on anyone's critical path.
+    // `dq_drained` is signalled as soon as the LAST TMEM read has landed; `stage_free` (which gates the producer's
+    // next load into this dO stage) once the last TMA read of the staging buffers has finished.
     for (int it = 0; it < n_iter; ++it) {
-      const int i = i_min + it;
+      const int i = i_min + it, st = it & 1;
+      uint8_t* dq_smem = Cfg::kStageInDO ? do_smem + st * Cfg::kTileBytes : smem + Cfg::kOffStage;
       mbar_wait(&bars[kBarDQFull], it & 1);
+      if constexpr (Cfg::kStageInDO)
+        mbar_wait(&bars[kBarDOEmpty0 + st], (it >> 1) & 1);  // dV(it) (other MMA stream) has finished reading dO(it)
       tc_fence_after();
 #pragma unroll
-      for (int ch = 0; ch < D / 32; ++ch) {
-        uint8_t* buf = dq_smem + (ch & 1) * Cfg::kDqStageBytes;
-        if (row == 0) tma_store_wait_read<1>();  // the reduce that last used this buffer has read it
-        named_bar_sync(3, 128);
-        float v[32];
-        tmem_ld32(tmem_base + lane_sel + kColDPT + ch * 32, reinterpret_cast<uint32_t*>(v));
+      for (int half = 0; half < D / 64; ++half) {
+        float v[64];
+        tmem_ld32(tmem_base + lane_sel + kColDPT + half * 64, reinterpret_cast<uint32_t*>(v));
+        tmem_ld32(tmem_base + lane_sel + kColDPT + half * 64 + 32, reinterpret_cast<uint32_t*>(v) + 32);
         tc_wait_ld();
-        if (ch == D / 32 - 1) {
+        if (half == D / 64 - 1) {
           tc_fence_before();
           mbar_arrive(&bars[kBarDQDrained]);
         }
-        uint8_t* rowp = buf + row * 128;
+        if (half > 0) {  // the two staging buffers are still being read by the first half's reduce
+          if (row == 0) tma_store_wait_read<0>();
+          named_bar_sync(3, 128);
+        }
 #pragma unroll
-        for (int c = 0; c < 8; ++c)
-          *reinterpret_cast<float4*>(rowp + ((c ^ (row & 7)) << 4)) =
-              make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+        for (int cb = 0; cb < 2; ++cb) {
+          uint8_t* rowp = dq_smem + cb * Cfg::kDqStageBytes + row * 128;
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+            *reinterpret_cast<float4*>(rowp + ((c ^ (row & 7)) << 4)) =
+                make_float4(v[cb * 32 + 4 * c], v[cb * 32 + 4 * c + 1], v[cb * 32 + 4 * c + 2], v[cb * 32 + 4 * c + 3]);
+        }
         fence_proxy_async_smem();
         named_bar_sync(3, 128);
         if (row == 0) {
-          tma_reduce_add_3d(&tm_dq, buf, ch * 32, i * kT, bh);
+#ifndef FA_BWD_EXPERIMENT_NO_DQ_REDUCE  // timing experiment only: results are wrong without it
+          tma_reduce_add_3d(&tm_dq, dq_smem, half * 64, i * kT, bh);
+          tma_reduce_add_3d(&tm_dq, dq_smem + Cfg::kDqStageBytes, half * 64 + 32, i * kT, bh);
+#endif
           tma_store_commit();
         }
+      }
+      if (row == 0) {
+        tma_store_wait_read<0>();
+        mbar_arrive(&bars[kBarStageFree0 + st]);
       }
     }
     if (row == 0) tma_store_wait_all<0>();
