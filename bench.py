@@ -398,7 +398,9 @@ def run_ring(args, workload, name):
     dev = torch.device("cuda", local)
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
     os.environ.setdefault("MASTER_PORT", "29531")
-    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    # NCCL's copy kernels compete with thousands of attention CTAs for SM slots: put them on a high-priority stream
+    opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev, pg_options=opts)
     from dist.ring import ring_attention
 
     b, h, n, d, causal = workload
