@@ -167,6 +167,23 @@ def time_cpu(kind, workload, steps, warmup, budget_s=25.0):
                       f"throughput is per-slice work / time, slices are independent"}
 
 
+def time_cpu_c1(kind):
+    """BASELINE configs[0] exactly: B2 H4 N512 d64 fp32, causal and non-causal, fwd+bwd on the host cores."""
+    out = {}
+    for causal in (False, True):
+        step, used = cpu_step_fn(kind, 512, 64, causal, 8)
+        step()
+        ts = []
+        for _ in range(5):
+            t0 = time.perf_counter()
+            step()
+            ts.append(time.perf_counter() - t0)
+        f_fwd, f_bwd = flops(2, 4, 512, 64, causal)
+        out["causal" if causal else "non_causal"] = {"min_ms": min(ts) * 1e3, "mean_ms": sum(ts) / len(ts) * 1e3,
+                                                     "tflops": (f_fwd + f_bwd) / min(ts) / 1e12, "kind": used}
+    return out
+
+
 def run_reference_arm(args, workload, name):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -183,6 +200,7 @@ def run_reference_arm(args, workload, name):
                            "triangle (SURVEY D4) - same tile count, so the timing stands"},
         "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": res["value"], "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "c1_B2_H4_N512_d64_fp32": time_cpu_c1("reference"),
     }
     print(json.dumps(line), flush=True)
 
