@@ -18,7 +18,8 @@ K_b is its own diagonal block).  Partials are merged inside the forward kernel's
 Non-causal attention needs no zig-zag: every step is [all local q] x [visiting block].
 
 The schedule is written once as a generator that yields its communication requests, so the same code runs
-  * under ``torch.distributed`` (``TorchRingDriver``: batched isend/irecv, overlapped with compute), and
+  * under ``torch.distributed`` (``SymmMemRingDriver``: copy-engine peer copies out of symmetric memory over NVLink, the
+    default on GPUs; ``TorchRingDriver``: NCCL/gloo batched isend/irecv), both overlapped with compute, and
   * inside ONE process for all P ranks (``run_loopback``) — used by the single-GPU and CPU tests.
 The block operator is injected (``BlockOps``); the product default is the sm_100a library.  Tests may inject a CPU
 implementation — nothing in this module imports the oracle.
@@ -259,13 +260,118 @@ class TorchRingDriver:
             return stop.value
 
 
+class SymmMemRingDriver:
+    """Same coroutine protocol, but blocks move by COPY-ENGINE peer copies out of symmetric (peer-mapped) memory over
+    NVLink instead of NCCL's SM-resident send/recv kernels.  The attention kernels own every SM (one 200 KiB CTA each),
+    so NCCL's copy CTAs are starved until a kernel's tail and the exchange stops overlapping with compute once the
+    per-step compute gets short (measured: C5 at 8 GPUs is comm-bound at an effective ~70 GB/s with NCCL P2P, while an
+    idle-GPU NCCL exchange does 313 GiB/s and a copy-engine peer pull 675 GiB/s on the same box).
+
+    post(tensors): stage them into this rank's symmetric slot (HBM copy on the compute stream); then, on a side stream:
+    cross-rank barrier (every slot staged) -> pull the previous rank's slot into fresh local tensors (DMA).
+    wait(handle):  the compute stream waits for that pull.  Two slots per message signature; slot reuse is safe because
+    a rank reaches barrier n+1 only after its pull n, and post n+2 is issued after wait n+1."""
+
+    _drivers = {}
+
+    @classmethod
+    def get(cls, group=None):
+        import torch.distributed as dist
+
+        key = id(group or dist.group.WORLD)
+        if key not in cls._drivers:
+            cls._drivers[key] = cls(group)
+        return cls._drivers[key]
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+
+        self.dist = dist
+        self.group = group or dist.group.WORLD
+        self.rank = dist.get_rank(self.group)
+        self.world = dist.get_world_size(self.group)
+        self.prev = (self.rank - 1) % self.world
+        self.side = torch.cuda.Stream()
+        self.channels = {}
+
+    def _channel(self, tensors):
+        import torch.distributed._symmetric_memory as symm
+
+        sig = tuple((tuple(t.shape), t.dtype) for t in tensors)
+        ch = self.channels.get(sig)
+        if ch is None:
+            offs, total = [], 0
+            for t in tensors:
+                offs.append(total)
+                total += (t.numel() * t.element_size() + 255) // 256 * 256
+            buf = symm.empty(2 * total, dtype=torch.uint8, device=tensors[0].device)
+            hdl = symm.rendezvous(buf, self.group)
+            ch = {"hdl": hdl, "buf": buf, "offs": offs, "slot_bytes": total, "count": 0}
+            self.channels[sig] = ch
+        return ch
+
+    @staticmethod
+    def _views(ch, rank, slot, tensors):
+        return [ch["hdl"].get_buffer(rank, tuple(t.shape), t.dtype, (slot * ch["slot_bytes"] + off) // t.element_size())
+                for t, off in zip(tensors, ch["offs"])]
+
+    def _post(self, tensors):
+        tensors = [t.contiguous() for t in tensors]
+        ch = self._channel(tensors)
+        slot = ch["count"] & 1
+        ch["count"] += 1
+        main = torch.cuda.current_stream()
+        for dst, src in zip(self._views(ch, self.rank, slot, tensors), tensors):
+            dst.copy_(src)
+        staged = torch.cuda.Event()
+        staged.record(main)
+        recvs = [torch.empty_like(t) for t in tensors]
+        with torch.cuda.stream(self.side):
+            self.side.wait_event(staged)
+            ch["hdl"].barrier(channel=0)
+            for dst, src in zip(recvs, self._views(ch, self.prev, slot, tensors)):
+                dst.copy_(src)
+            done = torch.cuda.Event()
+            done.record(self.side)
+        for r in recvs:
+            r.record_stream(self.side)
+        return done, recvs
+
+    def run(self, coroutine: Coroutine) -> tuple:
+        try:
+            request = next(coroutine)
+            while True:
+                kind, payload = request
+                if kind == "post":
+                    reply = self._post(payload)
+                else:
+                    done, recvs = payload
+                    torch.cuda.current_stream().wait_event(done)
+                    reply = recvs
+                request = coroutine.send(reply)
+        except StopIteration as stop:
+            return stop.value
+
+
+def make_driver(example: torch.Tensor, group=None, transport: str = "auto"):
+    """'symm' = copy-engine peer copies over symmetric memory (CUDA only), 'nccl' = batched isend/irecv."""
+    import os
+
+    transport = os.environ.get("FA_RING_TRANSPORT", transport)
+    if transport == "auto":
+        transport = "symm" if example.is_cuda else "nccl"
+    if transport == "symm":
+        return SymmMemRingDriver.get(group)
+    return TorchRingDriver(group)
+
+
 # ----------------------------------------------------------------------------------------------------------------------
 # public API
 # ----------------------------------------------------------------------------------------------------------------------
 class _RingAttnFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, q, k, v, causal, softmax_scale, group, ops):
-        driver = TorchRingDriver(group)
+        driver = make_driver(q, group)
         ops = ops or cuda_block_ops()
         q, k, v = q.contiguous(), k.contiguous(), v.contiguous()
         o, lse = driver.run(ring_forward(ops, driver.rank, driver.world, q, k, v, bool(causal), float(softmax_scale)))
@@ -277,7 +383,7 @@ class _RingAttnFn(torch.autograd.Function):
     def backward(ctx, do, dlse):
         q, k, v, o, lse = ctx.saved_tensors
         causal, scale, group, ops = ctx.meta
-        driver = TorchRingDriver(group)
+        driver = make_driver(q, group)
         dq, dk, dv = driver.run(ring_backward(ops, driver.rank, driver.world, q, k, v, o, lse, do.contiguous(), causal,
                                               scale))
         return dq, dk, dv, None, None, None, None
