@@ -106,11 +106,28 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
     return i_min + r;
   };
 
-  if (threadIdx.x == 0) {
-    if (smem_u32(smem) & 1023u) {
-      printf("fa_sm100 bwd: dynamic smem base not 1024-aligned\n");
-      __trap();
-    }
+  if (threadIdx.x == 0 && (smem_u32(smem) & 1023u)) {
+    printf("fa_sm100 bwd: dynamic smem base not 1024-aligned\n");
+    __trap();
+  }
+  // loads of one query tile (Q + row statistics on q_full, dO on do_full)
+  auto issue_q_tile = [&](int it) {
+    const int i = tile_of(it), st = it & 1;
+    mbar_arrive_expect_tx(&bars[kBarQFull0 + st], Cfg::kTileBytes + 1024);
+    for (int c = 0; c < kChunks; ++c)
+      tma_load_3d(q_smem + st * Cfg::kTileBytes + c * kSub, &tm_q, &bars[kBarQFull0 + st], c * 64, i * kT, bh);
+    bulk_load_1d(stats_smem + st * 256, p.rowstats + (static_cast<long long>(bh) * p.nqt + i) * 256, 1024,
+                 &bars[kBarQFull0 + st]);
+  };
+  auto issue_do_tile = [&](int it) {
+    const int i = tile_of(it), st = it & 1;
+    mbar_arrive_expect_tx(&bars[kBarDOFull0 + st], Cfg::kTileBytes);
+    for (int c = 0; c < kChunks; ++c)
+      tma_load_3d(do_smem + st * Cfg::kTileBytes + c * kSub, &tm_do, &bars[kBarDOFull0 + st], c * 64, i * kT, bh);
+  };
+  // The producer lane initialises the barriers and starts K, V and the first two query tiles BEFORE the block-wide
+  // sync, so their TMA latency overlaps the TMEM allocation and the rest of the prologue.
+  if (warp == 12 && lane == 0) {
     for (int b = 0; b < kBarCount; ++b) {
       uint32_t count = 1u;
       if (b == kBarPReady || b == kBarDSReady) count = 256u;
@@ -121,13 +138,20 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
       mbar_init(&bars[b], count);
     }
     fence_mbar_init();
-  }
-  if (warp == 12 && lane == 0) {
     tma_prefetch_desc(&tm_q);
     tma_prefetch_desc(&tm_k);
     tma_prefetch_desc(&tm_v);
     tma_prefetch_desc(&tm_do);
     tma_prefetch_desc(&tm_dq);
+    mbar_arrive_expect_tx(&bars[kBarKV], 2 * Cfg::kTileBytes);
+    for (int c = 0; c < kChunks; ++c) {
+      tma_load_3d(k_smem + c * kSub, &tm_k, &bars[kBarKV], c * 64, j * kT, bh);
+      tma_load_3d(v_smem + c * kSub, &tm_v, &bars[kBarKV], c * 64, j * kT, bh);
+    }
+    for (int it = 0; it < n_iter && it < 2; ++it) {
+      issue_q_tile(it);
+      issue_do_tile(it);
+    }
   }
   if (warp == 13) {
     tmem_alloc(tmem_slot, 512);
@@ -141,26 +165,15 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
 
   if (warp == 12) {
     // ===================================== TMA producer =====================================
-    if (lane == 0) {
-      mbar_arrive_expect_tx(&bars[kBarKV], 2 * Cfg::kTileBytes);
-      for (int c = 0; c < kChunks; ++c) {
-        tma_load_3d(k_smem + c * kSub, &tm_k, &bars[kBarKV], c * 64, j * kT, bh);
-        tma_load_3d(v_smem + c * kSub, &tm_v, &bars[kBarKV], c * 64, j * kT, bh);
-      }
-      for (int it = 0; it < n_iter; ++it) {
-        const int i = tile_of(it), st = it & 1;
+    if (lane == 0) {  // K, V and query tiles 0, 1 were issued in the prologue
+      for (int it = 2; it < n_iter; ++it) {
+        const int st = it & 1;
         mbar_wait(&bars[kBarQEmpty0 + st], ((it >> 1) & 1) ^ 1);
-        mbar_arrive_expect_tx(&bars[kBarQFull0 + st], Cfg::kTileBytes + 1024);
-        for (int c = 0; c < kChunks; ++c)
-          tma_load_3d(q_smem + st * Cfg::kTileBytes + c * kSub, &tm_q, &bars[kBarQFull0 + st], c * 64, i * kT, bh);
-        bulk_load_1d(stats_smem + st * 256, p.rowstats + (static_cast<long long>(bh) * p.nqt + i) * 256, 1024,
-                     &bars[kBarQFull0 + st]);
+        issue_q_tile(it);
         mbar_wait(&bars[kBarDOEmpty0 + st], ((it >> 1) & 1) ^ 1);     // dV / dP of the previous user are done ...
         if constexpr (Cfg::kStageInDO)
           mbar_wait(&bars[kBarStageFree0 + st], ((it >> 1) & 1) ^ 1);  // ... and so is the dQ reduce staged in this buffer
-        mbar_arrive_expect_tx(&bars[kBarDOFull0 + st], Cfg::kTileBytes);
-        for (int c = 0; c < kChunks; ++c)
-          tma_load_3d(do_smem + st * Cfg::kTileBytes + c * kSub, &tm_do, &bars[kBarDOFull0 + st], c * 64, i * kT, bh);
+        issue_do_tile(it);
       }
     }
     __syncwarp();

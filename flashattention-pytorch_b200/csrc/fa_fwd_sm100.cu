@@ -100,7 +100,9 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
   const int ntmax = nt0 > nt1 ? nt0 : nt1;   // steps
   const int n_kv_tiles = (ntmax + 1) >> 1;   // 128-row K/V tiles to stream
 
-  if (threadIdx.x == 0) {
+  // The producer lane initialises the barriers and starts the first loads (Q and up to NS K/V tiles) BEFORE the
+  // block-wide sync, so the TMA latency overlaps the TMEM allocation and the rest of the prologue.
+  if (warp == 8 && lane == 0) {
     for (int i = 0; i < 2; ++i) mbar_init(&q_full[i], 1);
     for (int i = 0; i < 4; ++i) {
       mbar_init(&s_full[i], 1);
@@ -112,12 +114,21 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
       mbar_init(&kv_empty[i], 2);  // both MMA warps release every stage
     }
     fence_mbar_init();
-  }
-  if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&tm_q);
     tma_prefetch_desc(&tm_k);
     tma_prefetch_desc(&tm_v);
     tma_prefetch_desc(&tm_o);
+    for (int i = 0; i < 2; ++i) {
+      mbar_arrive_expect_tx(&q_full[i], Cfg::kTileBytes);
+      for (int c = 0; c < kChunks; ++c)
+        tma_load_3d(q_smem + i * Cfg::kTileBytes + c * kSub, &tm_q, &q_full[i], c * 64, row0_t0 + i * kBM, bh);
+    }
+    for (int t = 0; t < 2 * n_kv_tiles && t < NS; ++t) {
+      mbar_arrive_expect_tx(&kv_full[t], Cfg::kTileBytes);
+      const CUtensorMap* tm = (t & 1) ? &tm_v : &tm_k;
+      for (int c = 0; c < kChunks; ++c)
+        tma_load_3d(kv_smem + t * Cfg::kTileBytes + c * kSub, tm, &kv_full[t], c * 64, (t >> 1) * kBN, bh);
+    }
   }
   if (warp == 9) {
     tmem_alloc(tmem_slot, 512);
@@ -130,13 +141,8 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
 
   if (warp == 8) {
     // ===================================== TMA producer =====================================
-    if (lane == 0) {
-      for (int i = 0; i < 2; ++i) {
-        mbar_arrive_expect_tx(&q_full[i], Cfg::kTileBytes);
-        for (int c = 0; c < kChunks; ++c)
-          tma_load_3d(q_smem + i * Cfg::kTileBytes + c * kSub, &tm_q, &q_full[i], c * 64, row0_t0 + i * kBM, bh);
-      }
-      for (int t = 0; t < 2 * n_kv_tiles; ++t) {
+    if (lane == 0) {  // slots 0..NS-1 (and Q) were issued in the prologue
+      for (int t = NS; t < 2 * n_kv_tiles; ++t) {
         const int stage = t % NS;
         mbar_wait(&kv_empty[stage], ((t / NS) & 1) ^ 1);
         mbar_arrive_expect_tx(&kv_full[stage], Cfg::kTileBytes);
@@ -237,11 +243,12 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
     const uint32_t t_s = tmem_base + lane_sel + wg * kBN;
     const uint32_t t_o = tmem_base + lane_sel + 256 + wg * D;
     const float c = p.scale_log2;
-    // largest visible key index for this row, in slice-local coordinates
-    long long vis = p.n_kv - 1;
+    // largest visible key index for this row, in slice-local coordinates (fits an int: n_kv, |diag| <= 2^30, and a
+    // row that sees nothing is clamped to -1)
+    int vis = p.n_kv - 1;
     if (p.causal) {
       const long long cv = static_cast<long long>(row_l) + p.diag;
-      vis = cv < vis ? cv : vis;
+      vis = cv < vis ? static_cast<int>(cv < -1 ? -1 : cv) : vis;
     }
 
     float m_ref = -INFINITY;  // reference max (raw score units) all stored exponentials are relative to
@@ -257,9 +264,8 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
       tmem_ld32(t_sb + 32, reinterpret_cast<uint32_t*>(s) + 32);
       tc_wait_ld();
 
-      const long long lim_ll = vis - static_cast<long long>(j) * kStep;
-      if (lim_ll < kStep - 1) {
-        const int lim = lim_ll < -1 ? -1 : static_cast<int>(lim_ll);
+      const int lim = vis - j * kStep;  // last visible column of this step (may be negative: nothing visible)
+      if (lim < kStep - 1) {
 #pragma unroll
         for (int x = 0; x < kStep; ++x) s[x] = (x > lim) ? -INFINITY : s[x];
       }
