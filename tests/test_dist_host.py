@@ -126,7 +126,8 @@ def _gloo_worker(rank, world, port, causal, q, k, v, do, out_queue):
         ql, kl, vl, dol = (split(t, world)[rank].requires_grad_(t is not do) for t in (q, k, v, do))
         o, lse = ring_attention(ql, kl, vl, causal=causal, ops=CPU_OPS)
         o.backward(dol)
-        out_queue.put((rank, o.detach(), lse.detach(), ql.grad, kl.grad, vl.grad))
+        # plain numpy (pickled by value): torch tensors travel as shared-memory handles that vanish when this process exits
+        out_queue.put((rank,) + tuple(t.detach().numpy().copy() for t in (o, lse, ql.grad, kl.grad, vl.grad)))
         dist.barrier()
     finally:
         dist.destroy_process_group()
@@ -144,6 +145,7 @@ def test_ring_attention_gloo_world2(causal):
     for p in procs:
         p.start()
     got = sorted((queue.get(timeout=120) for _ in range(world)), key=lambda t: t[0])
+    got = [(g[0],) + tuple(torch.from_numpy(a) for a in g[1:]) for g in got]
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
