@@ -446,11 +446,13 @@ static int launch_fwd(const Geometry& g, const void* q, const void* k, const voi
   p.scale_log2 = g.scale * 1.4426950408889634f;
 
   auto kern = fa_fwd_kernel<D, kBF16>;
-  static bool attr_set = false;  // benign race: idempotent
-  if (!attr_set) {
+  static bool attr_set[64];  // per device (function attributes are per context); benign race: idempotent
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes) != cudaSuccess)
       return FA_SM100_ELAUNCH;
-    attr_set = true;
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
   const long long nblocks = static_cast<long long>(p.npairs) * g.bh;
   if (nblocks > 0x7fffffffll) return FA_SM100_EINVAL_SHAPE;

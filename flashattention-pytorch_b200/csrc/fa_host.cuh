@@ -83,13 +83,13 @@ inline int check_shape(const fa_sm100_shape* s, Geometry* g) {
 }
 
 inline int check_device() {
-  static int cached = 1;  // 1 = unknown
-  if (cached != 1) return cached;
+  static int cached[64];  // 0 = unknown, 1 = sm_100, 2 = something else (benign race: idempotent writes)
   int dev = 0, major = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return FA_SM100_EDEVICE;
+  if (dev >= 0 && dev < 64 && cached[dev]) return cached[dev] == 1 ? FA_SM100_OK : FA_SM100_EDEVICE;
   if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return FA_SM100_EDEVICE;
-  cached = (major == 10) ? FA_SM100_OK : FA_SM100_EDEVICE;
-  return cached;
+  if (dev >= 0 && dev < 64) cached[dev] = (major == 10) ? 1 : 2;
+  return major == 10 ? FA_SM100_OK : FA_SM100_EDEVICE;
 }
 
 inline int launch_status() { return cudaGetLastError() == cudaSuccess ? FA_SM100_OK : FA_SM100_ELAUNCH; }
