@@ -188,6 +188,8 @@ def run_reference_arm(args, workload, name):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # torchrun exports OMP_NUM_THREADS=1; the reference arm is meant to use every host core it can
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
     b, h, n, d, causal = workload
     res = time_cpu("reference", workload, args.steps, args.warmup)
     line = {
