@@ -121,3 +121,56 @@ def test_errors_surface():
         ext.forward(h, h[:, :32], h, False, 0.125, 128, 128)
     with pytest.raises(RuntimeError):
         ext.fwd_raw(h, h, h, False, -1.0)
+
+
+@pytest.mark.parametrize("n_q,n_kv,causal", [(100, 300, False), (300, 100, False), (384, 128, True), (65, 1000, False)])
+def test_rectangular_attention(n_q, n_kv, causal):
+    """n_q != n_kv (what every ring step after the first looks like)."""
+    torch.manual_seed(n_q + n_kv)
+    bh, d = 3, 128
+    q, do = (torch.randn(bh, n_q, d, device="cuda", dtype=torch.bfloat16) for _ in range(2))
+    k, v = (torch.randn(bh, n_kv, d, device="cuda", dtype=torch.bfloat16) for _ in range(2))
+    q_row0 = n_kv - n_q if causal and n_kv > n_q else 0  # align the last query with the last key
+    o, lse = ext.fwd_raw(q, k, v, causal, 0.1, q_row0=q_row0)
+    dq, dk, dv = ext.bwd_raw(q, k, v, o, do, lse, causal, 0.1, q_row0=q_row0)
+    dq_r, dk_r, dv_r, o_r, lse_r = dense_backward_fp32(q.cpu(), k.cpu(), v.cpu(), do.cpu(), causal, 0.1, q_row0, 0)
+    for name, got, want, tol in (("o", o, o_r, 5e-2), ("lse", lse, lse_r, 1e-3), ("dq", dq, dq_r, 5e-2),
+                                 ("dk", dk, dk_r, 5e-2), ("dv", dv, dv_r, 5e-2)):
+        rep = error_report(got, want, tol, tol)
+        assert rep["violations"] == 0, f"{name}: {rep}"
+
+
+def test_strided_views_of_a_longer_sequence():
+    """Rows [s, e) of a longer (bh, N, d) tensor addressed in place through the slice stride (no copy)."""
+    torch.manual_seed(11)
+    bh, n, d, s, e = 4, 640, 64, 128, 512
+    big = [torch.randn(bh, n, d, device="cuda", dtype=torch.float16) for _ in range(4)]
+    q, k, v, do = (t[:, s:e] for t in big)
+    assert not q.is_contiguous()
+    o = torch.empty_like(big[0])[:, s:e]
+    lse = torch.empty(bh, n, device="cuda", dtype=torch.float32)[:, s:e]
+    ext.fwd_raw(q, k, v, True, 0.125, out=o, lse=lse)
+    o_c, lse_c = ext.fwd_raw(q.contiguous(), k.contiguous(), v.contiguous(), True, 0.125)
+    assert torch.equal(o, o_c) and torch.equal(lse, lse_c)
+    acc = torch.zeros(bh, n, d, device="cuda", dtype=torch.float32)[:, s:e]
+    stats = ext.bwd_prepare_raw(o, do, lse)
+    _, dk, dv = ext.bwd_raw(q, k, v, None, do, None, True, 0.125, rowstats=stats, dq_accum=acc)
+    dq = ext.dq_finish_raw(acc, torch.float16, 0.125)
+    dq_c, dk_c, dv_c = ext.bwd_raw(q.contiguous(), k.contiguous(), v.contiguous(), o_c, do.contiguous(), lse_c, True,
+                                   0.125)
+    assert torch.equal(dk, dk_c) and torch.equal(dv, dv_c)
+    assert (dq.float() - dq_c.float()).abs().max() < 1e-2
+
+
+def test_many_small_slices():
+    """batch*heads far beyond the SM count and beyond 65535 (1-D grid indexing)."""
+    torch.manual_seed(12)
+    bh, n, d = 70000, 16, 64
+    q, k, v = (torch.randn(bh, n, d, device="cuda", dtype=torch.bfloat16) for _ in range(3))
+    o, lse = ext.fwd_raw(q, k, v, True, 0.125)
+    sl = [0, 1, 65535, 65536, 69999]
+    from oracle.attention_oracle import dense_forward
+
+    o_r, lse_r = dense_forward(q[sl].cpu(), k[sl].cpu(), v[sl].cpu(), True, 0.125)
+    assert error_report(o[sl], o_r, 5e-2, 5e-2)["violations"] == 0
+    assert error_report(lse[sl], lse_r, 1e-3, 1e-3)["violations"] == 0
