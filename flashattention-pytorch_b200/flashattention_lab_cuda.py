@@ -66,6 +66,8 @@ ABI = {
     "fa_sm100_dq_finish": (ctypes.c_int, [_SP, _P, _P, _P]),
     "fa_sm100_cast_scaled": (ctypes.c_int, [_P, _P, ctypes.c_int64, ctypes.c_float, ctypes.c_int32, _P]),
     "fa_sm100_probe_umma": (ctypes.c_int, [ctypes.c_int, ctypes.c_int32, _P, _P, _P, _P]),
+    "fa_sm100_probe_reduce_rate": (ctypes.c_int, [_P, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, _P]),
+    "fa_sm100_probe_mma_rate": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, _P]),
 }
 
 
@@ -265,11 +267,34 @@ def cast_scaled(acc: torch.Tensor, alpha: float, dtype: torch.dtype) -> torch.Te
 
 def probe_umma(mode: int, a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     lib = load_library()
-    out = torch.empty((128, 128), device=a.device, dtype=torch.float32)
+    rows = 256 if int(mode) >= 4 else 128  # modes 4/5 drive a CTA pair: A and out have 256 rows
+    if tuple(a.shape) != (rows, 128) or tuple(b.shape) != (128, 128) or not (a.is_contiguous() and b.is_contiguous()):
+        raise ValueError(f"probe_umma mode {mode}: need contiguous a [{rows},128] and b [128,128]")
+    out = torch.empty((rows, 128), device=a.device, dtype=torch.float32)
     with torch.cuda.device(a.device):
         _check(lib.fa_sm100_probe_umma(int(mode), _dtype_code(a), a.data_ptr(), b.data_ptr(), out.data_ptr(),
                                        _stream_ptr(a)), "fa_sm100_probe_umma")
     return out
+
+
+def probe_mma_rate(pair: bool, a_from_tmem: bool, n: int, groups: int, ctas: int, device="cuda") -> None:
+    """Launch the tensor-core issue-rate probe on the current stream (the caller times it with CUDA events)."""
+    lib = load_library()
+    dev = torch.device(device)
+    with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        _check(lib.fa_sm100_probe_mma_rate(int(bool(pair)), int(bool(a_from_tmem)), int(n), int(groups), int(ctas),
+                                           stream), "fa_sm100_probe_mma_rate")
+
+
+def probe_reduce_rate(acc: torch.Tensor, nkt: int, rotate: bool = False) -> None:
+    """acc: [slices, nqt*128, 128] fp32, contiguous; every element grows by nkt (launch on the current stream)."""
+    lib = load_library()
+    if acc.dtype != torch.float32 or acc.dim() != 3 or acc.shape[2] != 128 or acc.shape[1] % 128 or not acc.is_contiguous():
+        raise ValueError("probe_reduce_rate: need contiguous fp32 acc [slices, nqt*128, 128]")
+    with torch.cuda.device(acc.device):
+        _check(lib.fa_sm100_probe_reduce_rate(acc.data_ptr(), acc.shape[0], acc.shape[1] // 128, int(nkt),
+                                              int(bool(rotate)), _stream_ptr(acc)), "fa_sm100_probe_reduce_rate")
 
 
 # ------------------------------------------------------------------------------------------------------------------

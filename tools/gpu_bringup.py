@@ -14,17 +14,20 @@ def stage_probe(mode, dtype_name):
 
     dt = getattr(torch, dtype_name)
     torch.manual_seed(mode)
-    a = torch.randn(128, 128, device="cuda", dtype=dt)
+    a = torch.randn(256 if mode >= 4 else 128, 128, device="cuda", dtype=dt)
     b = torch.randn(128, 128, device="cuda", dtype=dt)
     out = ext.probe_umma(mode, a, b)
     torch.cuda.synchronize()
     af, bf = a.float(), b.float()
-    want = {0: af @ bf.T, 1: af @ bf, 2: af @ bf, 3: af.T @ bf}[mode]
+    want = {0: lambda: af @ bf.T, 1: lambda: af @ bf, 2: lambda: af @ bf, 3: lambda: af.T @ bf,
+            4: lambda: af @ bf.T, 5: lambda: af @ bf}[mode]()
     err = (out - want).abs().max().item()
     print(f"probe mode={mode} {dtype_name}: max_abs_err={err:.4e} ref_max={want.abs().max().item():.2f}", flush=True)
     if err > 1e-2:
         # help diagnose layout mistakes: compare against a few plausible alternatives
-        alts = {"A@B.T": af @ bf.T, "A@B": af @ bf, "A.T@B": af.T @ bf, "A.T@B.T": af.T @ bf.T}
+        alts = {"A@B.T": af @ bf.T, "A@B": af @ bf}
+        if mode < 4:
+            alts.update({"A.T@B": af.T @ bf, "A.T@B.T": af.T @ bf.T})
         for name, alt in alts.items():
             print(f"    vs {name}: {(out - alt).abs().max().item():.4e}")
         print("    out[0,:8]", out[0, :8].tolist())
