@@ -66,14 +66,36 @@ def measured_peaks():
 # clocks sampling (nvidia-smi during the timed region)
 # ----------------------------------------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock / power / throttle reasons sampled DURING the timed region.  NVML in a thread (a sample every ~2 ms, so
+    even a 20 ms region gets several); `nvidia-smi -lms` as the fallback when the NVML bindings are unusable."""
     FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
               "clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index: int):
         self.index, self.rows, self.proc, self.thread = index, [], None, None
+        self.nvml, self.handle, self.stop_flag, self.sm_max = None, None, threading.Event(), None
+
+    def _physical_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        ids = [x for x in vis.split(",") if x.strip() != ""]
+        if ids and self.index < len(ids) and ids[self.index].strip().isdigit():
+            return int(ids[self.index])
+        return self.index
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index())
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+            self.thread = threading.Thread(target=self._poll_nvml, daemon=True)
+            self.thread.start()
+            return
+        except Exception:  # noqa: BLE001
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
                                           "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
@@ -83,23 +105,49 @@ class ClockSampler:
         self.thread = threading.Thread(target=self._read, daemon=True)
         self.thread.start()
 
+    def _poll_nvml(self):
+        n = self.nvml
+        bits = {"hw_slowdown": getattr(n, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                "hw_thermal_slowdown": getattr(n, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                "sw_thermal_slowdown": getattr(n, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                "sw_power_cap": getattr(n, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+        reasons_fn = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+            getattr(n, "nvmlDeviceGetCurrentClocksThrottleReasons")
+        while not self.stop_flag.is_set():
+            try:
+                sm = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+                pw = n.nvmlDeviceGetPowerUsage(self.handle) / 1000.0
+                mask = int(reasons_fn(self.handle))
+                flags = ["Active" if mask & bits[k] else "Not Active" for k in self.NAMES]
+                self.rows.append((time.time(), [str(sm), str(self.sm_max), str(pw), *flags]))
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(0.002)
+
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
 
     def stop(self, t0, t1):
-        if self.proc is None:
+        if self.nvml is not None:
+            self.stop_flag.set()
+            self.thread.join(timeout=1.0)
+            source, pad = "nvml", 0.0
+        elif self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+            source, pad = "nvidia-smi", 0.2
+        else:
             return None
-        time.sleep(0.15)
-        self.proc.terminate()
-        rows = [r for ts, r in self.rows if t0 <= ts <= t1 + 0.2] or [r for _, r in self.rows]
+        inside = [r for ts, r in self.rows if t0 <= ts <= t1 + pad]
+        rows = inside or [r for _, r in self.rows]
         if not rows:
             return None
         sm = [float(r[0]) for r in rows if r[0].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in rows for n, v in zip(names, r[3:7]) if v.lower().startswith("active")})
+        reasons = sorted({n for r in rows for n, v in zip(self.NAMES, r[3:7]) if v.lower().startswith("active")})
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": float(rows[0][1]),
-                "power_w_max": max(float(r[2]) for r in rows), "samples": len(rows), "reasons": reasons}
+                "power_w_max": max(float(r[2]) for r in rows), "samples": len(rows),
+                "samples_inside_timed_region": len(inside), "source": source, "reasons": reasons}
 
 
 # ----------------------------------------------------------------------------------------------------------------------

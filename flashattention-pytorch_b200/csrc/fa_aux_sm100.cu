@@ -348,9 +348,28 @@ fa_mma_rate_kernel(int n, int groups) {
 // query tiles of its slice (optionally starting at a rotated position) and TMA-reduce-adds a 128 x 128 fp32 tile
 // (four 128 x 32 boxes from two alternating pairs of staging buffers) into `acc` for each of them.
 __global__ void __launch_bounds__(128, 1)
-fa_reduce_rate_kernel(const __grid_constant__ CUtensorMap tm_acc, int nqt, int nkt, int rotate) {
+fa_reduce_rate_kernel(const __grid_constant__ CUtensorMap tm_acc, float* __restrict__ acc, int nqt, int nkt,
+                      int flags) {
   extern __shared__ __align__(1024) uint8_t smem_red[];
   const int slice = blockIdx.x / nkt, j = blockIdx.x % nkt;
+  const bool rotate = flags & 1, from_regs = flags & 2;
+  if (from_regs) {
+    // register path: thread = query row (as after a TMEM load).  Lane pairs split each 32-byte sector of a row between
+    // them, so one warp-wide red.v4 covers 16 rows x 32 contiguous bytes: full sectors, no shared-memory staging.
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int row_a = warp * 32 + (lane & ~1), row_b = row_a + 1, sub = (lane & 1) * 4;
+    for (int it = 0; it < nqt; ++it) {
+      int i = it + (rotate ? j : 0);
+      if (i >= nqt) i -= nqt;
+      float* base = acc + (static_cast<size_t>(slice) * nqt + i) * 128 * 128;
+#pragma unroll 4
+      for (int m = 0; m < 16; ++m) {
+        red_add_v4(base + row_a * 128 + m * 8 + sub, 1.f, 1.f, 1.f, 1.f);
+        red_add_v4(base + row_b * 128 + m * 8 + sub, 1.f, 1.f, 1.f, 1.f);
+      }
+    }
+    return;
+  }
   for (uint32_t i = threadIdx.x; i < 65536 / 4; i += 128) reinterpret_cast<float*>(smem_red)[i] = 1.0f;
   fence_proxy_async_smem();
   __syncthreads();
@@ -490,7 +509,7 @@ extern "C" int fa_sm100_probe_mma_rate(int pair, int a_from_tmem, int n, int gro
   return a_from_tmem ? launch_mma_rate<false, true>(n, groups, ctas, st) : launch_mma_rate<false, false>(n, groups, ctas, st);
 }
 
-extern "C" int fa_sm100_probe_reduce_rate(float* acc, int slices, int nqt, int nkt, int rotate, void* stream) {
+extern "C" int fa_sm100_probe_reduce_rate(float* acc, int slices, int nqt, int nkt, int flags, void* stream) {
   if (slices <= 0 || nqt <= 0 || nkt <= 0) return FA_SM100_EINVAL_SHAPE;
   if (!fa::aligned16(acc)) return FA_SM100_EINVAL_PTR;
   int rc = fa::check_device();
@@ -499,7 +518,8 @@ extern "C" int fa_sm100_probe_reduce_rate(float* acc, int slices, int nqt, int n
   const uint64_t rows = static_cast<uint64_t>(nqt) * 128;
   if ((rc = fa::make_tmap_3d(&tm, acc, fa::kElemF32, 128, rows, static_cast<uint64_t>(slices), rows * 128, 32, 128)))
     return rc;
-  cudaFuncSetAttribute(fa::fa_reduce_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
-  fa::fa_reduce_rate_kernel<<<slices * nkt, 128, 65536, static_cast<cudaStream_t>(stream)>>>(tm, nqt, nkt, rotate);
+  const int smem = (flags & 4) ? 200 * 1024 : 65536;  // flag 4: one CTA per SM, like the backward kernel
+  cudaFuncSetAttribute(fa::fa_reduce_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  fa::fa_reduce_rate_kernel<<<slices * nkt, 128, smem, static_cast<cudaStream_t>(stream)>>>(tm, acc, nqt, nkt, flags);
   return fa::launch_status();
 }

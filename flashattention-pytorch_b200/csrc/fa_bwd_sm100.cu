@@ -5,17 +5,17 @@
 // src/fa1/torch/impl.py:70-115, whose causal block rule `skip iff first key > last query` is the one used here):
 //   S = Q K^T * scale,  P = exp(S - lse),  dV += P^T dO,  dP = dO V^T,  dS = P o (dP - delta),
 //   dQ += dS K * scale,  dK += dS^T Q * scale.
-// Everything is computed TRANSPOSED (kv rows on TMEM lanes) so that P^T and dS^T are already in the layout the
-// tensor core wants for an A operand read straight from TMEM:
+// Everything is computed TRANSPOSED (kv rows on TMEM lanes) so that P^T is already in the layout the tensor core
+// wants for an A operand read straight from TMEM, and dS^T rows are what the compute threads write to shared memory:
 //   S^T  = K  Q^T      (A = K  smem K-major,  B = Q  smem K-major)            -> TMEM ST
 //   dP^T = V  dO^T     (A = V  smem K-major,  B = dO smem K-major)            -> TMEM DPT
 //   dV  += P^T  dO     (A = P^T  in TMEM,     B = dO smem MN-major)           -> TMEM DV
-//   dK  += dS^T Q      (A = dS^T in TMEM,     B = Q  smem MN-major)           -> TMEM DK
-//   dQ   = dS   K      (A = dS^T smem read MN-major, B = K smem MN-major)     -> TMEM DPT (aliases dP^T/dS^T)
+//   dQ   = dS   K      (A = dS^T smem read MN-major, B = K smem MN-major)     -> TMEM DPT (aliases dP^T)
+//   dK  += dS^T Q      (A = dS^T smem K-major, B = Q  smem MN-major)          -> TMEM DK
 // TMEM columns: ST [0,128)  DPT [128,256)  DV [256,256+D)  DK [256+D,256+2D).
 // Two independent MMA issue streams, one warp each, interleaved by the tensor pipe:
 //   stream X (owns the ST columns):   S^T(0) ; for each tile i:  [P(i) ready] dV(i) . S^T(i+1)
-//   stream Y (owns the DPT columns):  for each tile i:  [dQ(i-1) drained] dP^T(i) ; [dS(i) ready] dK(i) . dQ(i)
+//   stream Y (owns the DPT columns):  for each tile i:  [dQ(i-1) drained] dP^T(i) ; [dS(i) ready] dQ(i) . dK(i)
 // so neither chain waits for the other's softmax phase (a single in-order issuer made dP^T(i) queue behind dV(i)).
 //
 // Warps: 0-3 / 4-7 compute warpgroups (thread = kv row; WG0 takes query columns 0-63, WG1 64-127),
@@ -23,6 +23,24 @@
 //        12 TMA producer, 13 MMA stream X, 14 MMA stream Y.
 #include "ptx.cuh"
 #include "fa_host.cuh"
+
+// Optional per-phase timeline of one CTA (build with -DFA_BWD_TRACE; tools/bwd_trace.py reads it back).  clock64 is
+// the SM's cycle counter, so all warps of the traced CTA share one time base.
+#ifdef FA_BWD_TRACE
+#ifndef FA_BWD_TRACE_ITERS
+#define FA_BWD_TRACE_ITERS 64
+#endif
+#define FA_BWD_TRACE_EVENTS 16
+__device__ long long fa_bwd_trace_buf[FA_BWD_TRACE_EVENTS * FA_BWD_TRACE_ITERS];
+__device__ int fa_bwd_trace_block = 0;
+#define FA_TRACE(ev, it)                                                                       \
+  do {                                                                                         \
+    if (static_cast<int>(blockIdx.x) == fa_bwd_trace_block && (it) < FA_BWD_TRACE_ITERS)       \
+      fa_bwd_trace_buf[(ev) * FA_BWD_TRACE_ITERS + (it)] = clock64();                          \
+  } while (0)
+#else
+#define FA_TRACE(ev, it) do { } while (0)
+#endif
 
 namespace fa {
 
@@ -125,6 +143,18 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
     for (int c = 0; c < kChunks; ++c)
       tma_load_3d(do_smem + st * Cfg::kTileBytes + c * kSub, &tm_do, &bars[kBarDOFull0 + st], c * 64, i * kT, bh);
   };
+#ifndef FA_BWD_DK_FROM_SMEM
+#define FA_BWD_DK_FROM_SMEM 0  // 1: dQ issued before dK, dK reads dS^T from shared memory (measured: slower)
+#endif
+#ifndef FA_BWD_L2_AHEAD
+#define FA_BWD_L2_AHEAD 2  // tiles of L2 prefetch distance beyond the shared-memory ring
+#endif
+  auto prefetch_q_tile = [&](int it) {
+    for (int c = 0; c < kChunks; ++c) tma_prefetch_l2_3d(&tm_q, c * 64, tile_of(it) * kT, bh);
+  };
+  auto prefetch_do_tile = [&](int it) {
+    for (int c = 0; c < kChunks; ++c) tma_prefetch_l2_3d(&tm_do, c * 64, tile_of(it) * kT, bh);
+  };
   // The producer lane initialises the barriers and starts K, V and the first two query tiles BEFORE the block-wide
   // sync, so their TMA latency overlaps the TMEM allocation and the rest of the prologue.
   if (warp == 12 && lane == 0) {
@@ -152,6 +182,10 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
       issue_q_tile(it);
       issue_do_tile(it);
     }
+    for (int it = 2; it < n_iter && it < 2 + FA_BWD_L2_AHEAD; ++it) {
+      prefetch_q_tile(it);
+      prefetch_do_tile(it);
+    }
   }
   if (warp == 13) {
     tmem_alloc(tmem_slot, 512);
@@ -166,14 +200,35 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
   if (warp == 12) {
     // ===================================== TMA producer =====================================
     if (lane == 0) {  // K, V and query tiles 0, 1 were issued in the prologue
-      for (int it = 2; it < n_iter; ++it) {
-        const int st = it & 1;
-        mbar_wait(&bars[kBarQEmpty0 + st], ((it >> 1) & 1) ^ 1);
-        issue_q_tile(it);
-        mbar_wait(&bars[kBarDOEmpty0 + st], ((it >> 1) & 1) ^ 1);     // dV / dP of the previous user are done ...
-        if constexpr (Cfg::kStageInDO)
-          mbar_wait(&bars[kBarStageFree0 + st], ((it >> 1) & 1) ^ 1);  // ... and so is the dQ reduce staged in this buffer
-        issue_do_tile(it);
+      // Q and dO stages free up at different moments (Q(it) after dK(it); dO(it) only after the dQ(it) reduce staged in
+      // it has been read), so the two load sequences advance independently: polling both keeps a late dO stage from
+      // holding back the next Q tile, which heads the following iteration's critical path.
+      int q_next = 2, do_next = 2;
+      const long long t0 = clock64();
+      while (q_next < n_iter || do_next < n_iter) {
+        if (q_next < n_iter && mbar_test_wait(&bars[kBarQEmpty0 + (q_next & 1)], ((q_next >> 1) & 1) ^ 1)) {
+          issue_q_tile(q_next);
+          FA_TRACE(12, q_next);
+          if (q_next + FA_BWD_L2_AHEAD < n_iter) prefetch_q_tile(q_next + FA_BWD_L2_AHEAD);
+          ++q_next;
+        }
+        if (do_next < n_iter) {
+          const uint32_t par = ((do_next >> 1) & 1) ^ 1;
+          bool ok = mbar_test_wait(&bars[kBarDOEmpty0 + (do_next & 1)], par);  // dV / dP of the previous user are done
+          if constexpr (Cfg::kStageInDO)                                        // ... and so is the dQ reduce staged there
+            ok = ok && mbar_test_wait(&bars[kBarStageFree0 + (do_next & 1)], par);
+          if (ok) {
+            issue_do_tile(do_next);
+            FA_TRACE(13, do_next);
+            if (do_next + FA_BWD_L2_AHEAD < n_iter) prefetch_do_tile(do_next + FA_BWD_L2_AHEAD);
+            ++do_next;
+          }
+        }
+        if (clock64() - t0 > FA_WAIT_TIMEOUT_CYCLES) {
+          printf("fa_sm100 bwd: producer timeout (block %d, q_next %d, do_next %d of %d)\n", blockIdx.x, q_next, do_next,
+                 n_iter);
+          __trap();
+        }
       }
     }
     __syncwarp();
@@ -189,6 +244,7 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
       const uint32_t q_km = umma_desc_lo(smem_u32(q_smem), 16), do_km = umma_desc_lo(smem_u32(do_smem), 16);
       const uint32_t k_mn = umma_desc_lo(smem_u32(k_smem), kSub), q_mn = umma_desc_lo(smem_u32(q_smem), kSub);
       const uint32_t do_mn = umma_desc_lo(smem_u32(do_smem), kSub), ds_mn = umma_desc_lo(smem_u32(ds_smem), kT * 128);
+      const uint32_t ds_km = umma_desc_lo(smem_u32(ds_smem), 16);
 
       // D[kv, q] = A[kv, :] . B[q, :]   (both K-major, contraction over the head dim)
       auto mma_kmajor = [&](uint32_t d_col, uint32_t a_lo, uint32_t b_lo) {
@@ -215,6 +271,18 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
                   kk > 0 ? 1u : 0u);
       };
 
+      // dK[kv, d] (+)= dS^T[kv, q] . Q[q, d]   (A = the dS^T tile in shared memory read K-major, B = Q MN-major).
+      // dS^T is NOT kept in TMEM: it would sit in the DPT columns that dQ overwrites, forcing dK to run before dQ,
+      // and dQ -> drain -> dP^T(next) -> dS(next) -> dQ(next) is the loop that sets the iteration period.
+      auto mma_dk = [&](uint32_t b_lo, bool acc) {
+#pragma unroll
+        for (int kk = 0; kk < kT / 16; ++kk) {
+          const uint32_t off = (kk >> 2) * ((kT * 128) >> 4) + (kk & 3) * 2;
+          umma_ss(tmem_base + kColDK, umma_desc(ds_km + off), umma_desc(b_lo + kk * 128), idesc_acc,
+                  (acc || kk > 0) ? 1u : 0u);
+        }
+      };
+
       mbar_wait(&bars[kBarKV], 0);
       if (warp == 13) {
         // ---------------- stream X: S^T and dV ----------------
@@ -232,6 +300,7 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
           mbar_wait(&bars[kBarDOFull0 + st], (it >> 1) & 1);
           mbar_wait(&bars[kBarPReady], it & 1);
           tc_fence_after();
+          if (lane == 0) FA_TRACE(0, it);
           if (elect_one()) {
             mma_from_tmem(kColDV, kColST, do_mn + st * kTileLo, it > 0);  // dV(it) += P^T dO
             tc_commit(&bars[kBarDOEmpty0 + st]);
@@ -240,6 +309,7 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
           if (it + 1 < n_iter) {
             mbar_wait(&bars[kBarQFull0 + (st ^ 1)], ((it + 1) >> 1) & 1);
             tc_fence_after();
+            if (lane == 0) FA_TRACE(1, it);
             if (elect_one()) {
               // S^T(it+1): P^T(it) in the same columns has been consumed by dV(it) (in-order within this stream)
               mma_kmajor(kColST, k_km, q_km + (st ^ 1) * kTileLo);
@@ -256,6 +326,7 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
           mbar_wait(&bars[kBarDOFull0 + st], (it >> 1) & 1);
           if (it > 0) mbar_wait(&bars[kBarDQDrained], (it - 1) & 1);  // dP^T reuses the dQ(it-1) columns
           tc_fence_after();
+          if (lane == 0) FA_TRACE(2, it);
           if (elect_one()) {
             mma_kmajor(kColDPT, v_km, do_km + st * kTileLo);  // dP^T(it) = V dO^T
             tc_commit(&bars[kBarDPFull]);
@@ -265,11 +336,19 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
           mbar_wait(&bars[kBarQFull0 + st], (it >> 1) & 1);
           mbar_wait(&bars[kBarDSReady], it & 1);
           tc_fence_after();
+          if (lane == 0) FA_TRACE(3, it);
           if (elect_one()) {
-            mma_from_tmem(kColDK, kColDPT, q_mn + st * kTileLo, it > 0);  // dK(it) += dS^T Q
-            tc_commit(&bars[kBarQEmpty0 + st]);
-            mma_dq();                                                      // dQ(it) = dS K
+#if FA_BWD_DK_FROM_SMEM
+            mma_dq();                                       // dQ(it) = dS K: heads the next tile's critical path
             tc_commit(&bars[kBarDQFull]);
+            mma_dk(q_mn + st * kTileLo, it > 0);            // dK(it) += dS^T Q
+            tc_commit(&bars[kBarQEmpty0 + st]);
+#else
+            mma_from_tmem(kColDK, kColDPT, q_mn + st * kTileLo, it > 0);  // dK(it) += dS^T Q (reads dS^T before ...
+            tc_commit(&bars[kBarQEmpty0 + st]);
+            mma_dq();                                                      // ... dQ(it) = dS K overwrites it)
+            tc_commit(&bars[kBarDQFull]);
+#endif
           }
           __syncwarp();
         }
@@ -294,42 +373,69 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
       if constexpr (Cfg::kStageInDO)
         mbar_wait(&bars[kBarDOEmpty0 + st], (it >> 1) & 1);  // dV(it) (other MMA stream) has finished reading dO(it)
       tc_fence_after();
+      if (row == 0) FA_TRACE(8, it);
+      float v[64];
+      // 32 fp32 columns of this row -> one 128-byte swizzled row of staging buffer `cb`
+      auto stage_chunk = [&](int cb, int off) {
+        uint8_t* rowp = dq_smem + cb * Cfg::kDqStageBytes + row * 128;
 #pragma unroll
-      for (int half = 0; half < D / 64; ++half) {
-        float v[64];
-        tmem_ld32(tmem_base + lane_sel + kColDPT + half * 64, reinterpret_cast<uint32_t*>(v));
-        tmem_ld32(tmem_base + lane_sel + kColDPT + half * 64 + 32, reinterpret_cast<uint32_t*>(v) + 32);
+        for (int c = 0; c < 8; ++c)
+          *reinterpret_cast<float4*>(rowp + ((c ^ (row & 7)) << 4)) =
+              make_float4(v[off + 4 * c], v[off + 4 * c + 1], v[off + 4 * c + 2], v[off + 4 * c + 3]);
+      };
+      auto reduce_chunk = [&](int cb, int col) {
+#ifndef FA_BWD_EXPERIMENT_NO_DQ_REDUCE  // timing experiment only: results are wrong without it
+        tma_reduce_add_3d(&tm_dq, dq_smem + cb * Cfg::kDqStageBytes, col, i * kT, bh);
+#endif
+        tma_store_commit();
+      };
+      tmem_ld32(tmem_base + lane_sel + kColDPT, reinterpret_cast<uint32_t*>(v));
+      tmem_ld32(tmem_base + lane_sel + kColDPT + 32, reinterpret_cast<uint32_t*>(v) + 32);
+      tc_wait_ld();
+      stage_chunk(0, 0);
+      stage_chunk(1, 32);
+      if constexpr (D == 128) {  // second 64 columns straight away: the accumulator goes back before any TMA bookkeeping
+        tmem_ld32(tmem_base + lane_sel + kColDPT + 64, reinterpret_cast<uint32_t*>(v));
+        tmem_ld32(tmem_base + lane_sel + kColDPT + 96, reinterpret_cast<uint32_t*>(v) + 32);
         tc_wait_ld();
-        if (half == D / 64 - 1) {
-          tc_fence_before();
-          mbar_arrive(&bars[kBarDQDrained]);
+      }
+      tc_fence_before();
+      mbar_arrive(&bars[kBarDQDrained]);
+      if (row == 0) FA_TRACE(9, it);
+      fence_proxy_async_smem();
+      named_bar_sync(3, 128);
+      if (row == 0) {
+        reduce_chunk(0, 0);
+        reduce_chunk(1, 32);
+      }
+      if constexpr (D == 128) {
+        // columns 64-127 follow through the same two buffers, each as soon as its previous reduce has been read, so
+        // the reduce engine (about 40 B/ns per SM, measured) never waits for the staging stores of a whole half
+        if (row == 0) {
+          tma_store_wait_read<1>();
+          FA_TRACE(10, it);
         }
-        if (half > 0) {  // the two staging buffers are still being read by the first half's reduce
-          if (row == 0) tma_store_wait_read<0>();
-          named_bar_sync(3, 128);
-        }
-#pragma unroll
-        for (int cb = 0; cb < 2; ++cb) {
-          uint8_t* rowp = dq_smem + cb * Cfg::kDqStageBytes + row * 128;
-#pragma unroll
-          for (int c = 0; c < 8; ++c)
-            *reinterpret_cast<float4*>(rowp + ((c ^ (row & 7)) << 4)) =
-                make_float4(v[cb * 32 + 4 * c], v[cb * 32 + 4 * c + 1], v[cb * 32 + 4 * c + 2], v[cb * 32 + 4 * c + 3]);
-        }
+        named_bar_sync(3, 128);
+        stage_chunk(0, 0);
         fence_proxy_async_smem();
         named_bar_sync(3, 128);
         if (row == 0) {
-#ifndef FA_BWD_EXPERIMENT_NO_DQ_REDUCE  // timing experiment only: results are wrong without it
-          tma_reduce_add_3d(&tm_dq, dq_smem, half * 64, i * kT, bh);
-          tma_reduce_add_3d(&tm_dq, dq_smem + Cfg::kDqStageBytes, half * 64 + 32, i * kT, bh);
-#endif
-          tma_store_commit();
+          reduce_chunk(0, 64);
+          tma_store_wait_read<1>();
         }
+        named_bar_sync(3, 128);
+        stage_chunk(1, 32);
+        fence_proxy_async_smem();
+        named_bar_sync(3, 128);
+        if (row == 0) reduce_chunk(1, 96);
       }
       if (row == 0) {
+        FA_TRACE(14, it);
         tma_store_wait_read<0>();
         mbar_arrive(&bars[kBarStageFree0 + st]);
+        FA_TRACE(11, it);
       }
+      if constexpr (!Cfg::kStageInDO) named_bar_sync(3, 128);  // dedicated staging is reused by the very next tile
     }
     if (row == 0) tma_store_wait_all<0>();
   } else if (warp < 8) {
@@ -356,6 +462,14 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
       mbar_wait(&bars[kBarQFull0 + st], (it >> 1) & 1);  // row statistics ride on the Q barrier
       mbar_wait(&bars[kBarSFull], it & 1);
       tc_fence_after();
+      if (threadIdx.x == 0) FA_TRACE(4, it);
+#ifdef FA_BWD_TRACE
+      if (threadIdx.x == 0 && static_cast<int>(blockIdx.x) == fa_bwd_trace_block && it < FA_BWD_TRACE_ITERS) {
+        long long gt;  // wall-clock ns next to the cycle stamp: calibrates the SM clock under load
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        fa_bwd_trace_buf[15 * FA_BWD_TRACE_ITERS + it] = gt;
+      }
+#endif
       float pr[64];
       const float2 c2 = make_float2(p.scale_log2, p.scale_log2);
 #pragma unroll
@@ -384,38 +498,52 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
       tc_wait_st();
       tc_fence_before();
       mbar_arrive(&bars[kBarPReady]);
+      if (threadIdx.x == 0) FA_TRACE(5, it);
 
       mbar_wait(&bars[kBarDPFull], it & 1);
       tc_fence_after();
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        float dp[32];
-        tmem_ld32(t_dpt + c * 32, reinterpret_cast<uint32_t*>(dp));
+      if (threadIdx.x == 0) FA_TRACE(6, it);
+      {
+        // dS^T = P o (dP^T - delta) in four 16-column steps; the TMEM load of step c+1 is in flight while step c is
+        // computed, converted and written to the shared-memory tile (the only copy: dK and dQ both read it from there)
+        float dp[2][16];
+        tmem_ld16(t_dpt, reinterpret_cast<uint32_t*>(dp[0]));
         tc_wait_ld();
-        uint32_t pk[16];
 #pragma unroll
-        for (int x4 = 0; x4 < 8; ++x4) {
-          const float4 d4 = *reinterpret_cast<const float4*>(dl + c * 32 + x4 * 4);  // -delta
-          const int x = x4 * 4;
-          const float2 a = fmul2(make_float2(pr[c * 32 + x], pr[c * 32 + x + 1]),
-                                 fadd2(make_float2(dp[x], dp[x + 1]), make_float2(d4.x, d4.y)));
-          const float2 b = fmul2(make_float2(pr[c * 32 + x + 2], pr[c * 32 + x + 3]),
-                                 fadd2(make_float2(dp[x + 2], dp[x + 3]), make_float2(d4.z, d4.w)));
-          pk[x >> 1] = pack2<kBF16>(a.x, a.y);
-          pk[(x >> 1) + 1] = pack2<kBF16>(b.x, b.y);
-        }
-        tmem_st16(t_dpt + c * 16, pk);
+        for (int c = 0; c < 4; ++c) {
+          if (c + 1 < 4) tmem_ld16(t_dpt + (c + 1) * 16, reinterpret_cast<uint32_t*>(dp[(c + 1) & 1]));
+          const float* dpc = dp[c & 1];
+          uint32_t pk[8];
 #pragma unroll
-        for (int ch = 0; ch < 4; ++ch) {
-          const int chunk = c * 4 + ch;
-          *reinterpret_cast<uint4*>(ds_row + ((chunk ^ (r & 7)) << 4)) =
-              make_uint4(pk[4 * ch], pk[4 * ch + 1], pk[4 * ch + 2], pk[4 * ch + 3]);
+          for (int x4 = 0; x4 < 4; ++x4) {
+            const float4 d4 = *reinterpret_cast<const float4*>(dl + c * 16 + x4 * 4);  // -delta
+            const int x = x4 * 4;
+            const float2 a = fmul2(make_float2(pr[c * 16 + x], pr[c * 16 + x + 1]),
+                                   fadd2(make_float2(dpc[x], dpc[x + 1]), make_float2(d4.x, d4.y)));
+            const float2 b = fmul2(make_float2(pr[c * 16 + x + 2], pr[c * 16 + x + 3]),
+                                   fadd2(make_float2(dpc[x + 2], dpc[x + 3]), make_float2(d4.z, d4.w)));
+            pk[x >> 1] = pack2<kBF16>(a.x, a.y);
+            pk[(x >> 1) + 1] = pack2<kBF16>(b.x, b.y);
+          }
+#pragma unroll
+          for (int ch = 0; ch < 2; ++ch) {
+            const int chunk = c * 2 + ch;
+            *reinterpret_cast<uint4*>(ds_row + ((chunk ^ (r & 7)) << 4)) =
+                make_uint4(pk[4 * ch], pk[4 * ch + 1], pk[4 * ch + 2], pk[4 * ch + 3]);
+          }
+          if (c + 1 < 4) tc_wait_ld();
+#if !FA_BWD_DK_FROM_SMEM
+          tmem_st8(t_dpt + c * 8, pk);  // packed dS^T over the dP^T columns this thread has already consumed
+#endif
         }
       }
+#if !FA_BWD_DK_FROM_SMEM
       tc_wait_st();
+#endif
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(&bars[kBarDSReady]);
+      if (threadIdx.x == 0) FA_TRACE(7, it);
     }
 
     // ------------------------------- epilogue: WG0 stores dV, WG1 stores dK * scale -------------------------------
@@ -609,3 +737,17 @@ extern "C" int fa_sm100_bwd(const fa_sm100_shape* s, const void* q, const void* 
   return g.dtype == FA_SM100_DTYPE_BF16 ? fa::launch_bwd<64, true>(g, q, k, v, d_o, rowstats, dq_accum, dk, dv, st)
                                         : fa::launch_bwd<64, false>(g, q, k, v, d_o, rowstats, dq_accum, dk, dv, st);
 }
+
+#ifdef FA_BWD_TRACE
+// debug build only: select the CTA to trace / copy its timeline (events x FA_BWD_TRACE_ITERS clock64 values) to the host
+extern "C" int fa_sm100_debug_bwd_trace(int set_block, long long* host_dst, int max_values) {
+  if (set_block >= 0) {
+    long long zero[FA_BWD_TRACE_EVENTS * FA_BWD_TRACE_ITERS] = {};
+    cudaMemcpyToSymbol(fa_bwd_trace_buf, zero, sizeof(zero));
+    return cudaMemcpyToSymbol(fa_bwd_trace_block, &set_block, sizeof(int)) == cudaSuccess ? 0 : -1;
+  }
+  const int n = FA_BWD_TRACE_EVENTS * FA_BWD_TRACE_ITERS;
+  if (!host_dst || max_values < n) return -1;
+  return cudaMemcpyFromSymbol(host_dst, fa_bwd_trace_buf, n * sizeof(long long)) == cudaSuccess ? n : -1;
+}
+#endif

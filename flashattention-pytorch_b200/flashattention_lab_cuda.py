@@ -287,14 +287,15 @@ def probe_mma_rate(pair: bool, a_from_tmem: bool, n: int, groups: int, ctas: int
                                            stream), "fa_sm100_probe_mma_rate")
 
 
-def probe_reduce_rate(acc: torch.Tensor, nkt: int, rotate: bool = False) -> None:
-    """acc: [slices, nqt*128, 128] fp32, contiguous; every element grows by nkt (launch on the current stream)."""
+def probe_reduce_rate(acc: torch.Tensor, nkt: int, flags: int = 0) -> None:
+    """acc: [slices, nqt*128, 128] fp32, contiguous; every element grows by nkt (launch on the current stream).
+    flags: 1 rotated walk, 2 red.global.v4 from registers instead of TMA reduce, 4 one CTA per SM."""
     lib = load_library()
     if acc.dtype != torch.float32 or acc.dim() != 3 or acc.shape[2] != 128 or acc.shape[1] % 128 or not acc.is_contiguous():
         raise ValueError("probe_reduce_rate: need contiguous fp32 acc [slices, nqt*128, 128]")
     with torch.cuda.device(acc.device):
         _check(lib.fa_sm100_probe_reduce_rate(acc.data_ptr(), acc.shape[0], acc.shape[1] // 128, int(nkt),
-                                              int(bool(rotate)), _stream_ptr(acc)), "fa_sm100_probe_reduce_rate")
+                                              int(flags), _stream_ptr(acc)), "fa_sm100_probe_reduce_rate")
 
 
 # ------------------------------------------------------------------------------------------------------------------

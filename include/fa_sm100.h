@@ -125,10 +125,11 @@ int fa_sm100_probe_mma_rate(int pair, int a_from_tmem, int n, int groups, int ct
 /*
  * L2 reduce-add rate probe (measurement aid): the backward's dQ accumulation traffic with no compute around it.
  * slices * nkt CTAs; CTA (slice, j) reduce-adds a 128x128 fp32 tile of ones into each of the nqt row tiles of
- * acc[slice] (acc: slices x (nqt*128) x 128 fp32), starting at tile j when `rotate`.  Afterwards every element of
- * acc has grown by nkt.  Bytes reduced = slices * nkt * nqt * 65536.
+ * acc[slice] (acc: slices x (nqt*128) x 128 fp32).  flags: 1 = start at tile j (rotated walk), 2 = red.global.v4 from
+ * registers instead of TMA reduce from shared memory, 4 = one CTA per SM.  Afterwards every element of acc has grown
+ * by nkt.  Bytes reduced = slices * nkt * nqt * 65536.
  */
-int fa_sm100_probe_reduce_rate(float* acc, int slices, int nqt, int nkt, int rotate, void* stream);
+int fa_sm100_probe_reduce_rate(float* acc, int slices, int nqt, int nkt, int flags, void* stream);
 
 #ifdef __cplusplus
 }

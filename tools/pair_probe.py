@@ -14,7 +14,7 @@ ROOT = Path(__file__).resolve().parents[1]
 sys.path[:0] = [str(ROOT / "flashattention-pytorch_b200"), str(ROOT)]
 
 
-def stage_rate():
+def stage_rate(mma=True):
     import torch
     import flashattention_lab_cuda as ext
 
@@ -26,7 +26,7 @@ def stage_rate():
         (0, 0, 64), (0, 0, 128), (0, 0, 256), (0, 1, 64), (0, 1, 128),
         (1, 0, 64), (1, 0, 128), (1, 0, 256), (1, 1, 128),
     ]
-    for pair, ts, n in configs:
+    for pair, ts, n in (configs if mma else []):
         for _ in range(2):
             ext.probe_mma_rate(pair, ts, n, 256, ctas)
         torch.cuda.synchronize()
@@ -48,22 +48,25 @@ def stage_rate():
     # L2 reduce-add rate with the backward's dQ pattern (headline shape: 64 slices, N = 8192 -> 64 x 64 tiles)
     for slices, nqt, nkt in ((64, 64, 64), (64, 32, 32)):
         acc = torch.zeros(slices, nqt * 128, 128, device="cuda", dtype=torch.float32)
-        for rotate in (False, True):
-            ext.probe_reduce_rate(acc, nkt, rotate)
+        n_calls = 0
+        for flags in (0, 1, 4, 2, 3, 6):
+            ext.probe_reduce_rate(acc, nkt, flags)
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            ext.probe_reduce_rate(acc, nkt, rotate)
+            ext.probe_reduce_rate(acc, nkt, flags)
             e1.record()
             torch.cuda.synchronize()
+            n_calls += 2
             ms = e0.elapsed_time(e1)
             gb = slices * nkt * nqt * 65536 / 1e9
-            row = {"probe": "reduce_rate", "slices": slices, "nqt": nqt, "nkt": nkt, "rotate": rotate, "ms": ms,
+            row = {"probe": "reduce_rate", "slices": slices, "nqt": nqt, "nkt": nkt, "flags": flags, "ms": ms,
                    "gbytes": gb, "tb_per_s": gb / ms}
             rows.append(row)
-            print(f"reduce slices={slices} nqt={nqt} nkt={nkt} rotate={int(rotate)}: {gb:.1f} GB in {ms:.3f} ms = "
-                  f"{gb / ms:.2f} TB/s", flush=True)
-        want = 4.0 * nkt
+            print(f"reduce slices={slices} nqt={nqt} nkt={nkt} flags={flags} "
+                  f"({'regs' if flags & 2 else 'tma '}{' rot' if flags & 1 else ''}{' 1cta/sm' if flags & 4 else ''}): "
+                  f"{gb:.1f} GB in {ms:.3f} ms = {gb / ms:.2f} TB/s", flush=True)
+        want = float(n_calls * nkt)
         ok = bool((acc == want).all().item())
         print(f"  accumulated value check (every element == {want}): {ok}", flush=True)
         del acc
@@ -74,8 +77,8 @@ def stage_rate():
 
 
 def main():
-    if len(sys.argv) > 1 and sys.argv[1] == "rate":
-        sys.exit(stage_rate())
+    if len(sys.argv) > 1 and sys.argv[1] in ("rate", "reduce"):
+        sys.exit(stage_rate(mma=sys.argv[1] == "rate"))
     rc = 0
     for mode in (4, 5):
         for dt in ("bfloat16", "float16"):
