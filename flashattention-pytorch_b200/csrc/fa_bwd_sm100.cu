@@ -5,17 +5,17 @@
 // src/fa1/torch/impl.py:70-115, whose causal block rule `skip iff first key > last query` is the one used here):
 //   S = Q K^T * scale,  P = exp(S - lse),  dV += P^T dO,  dP = dO V^T,  dS = P o (dP - delta),
 //   dQ += dS K * scale,  dK += dS^T Q * scale.
-// Everything is computed TRANSPOSED (kv rows on TMEM lanes) so that P^T is already in the layout the tensor core
-// wants for an A operand read straight from TMEM, and dS^T rows are what the compute threads write to shared memory:
+// Everything is computed TRANSPOSED (kv rows on TMEM lanes) so that P^T and dS^T are already in the layout the
+// tensor core wants for an A operand read straight from TMEM:
 //   S^T  = K  Q^T      (A = K  smem K-major,  B = Q  smem K-major)            -> TMEM ST
 //   dP^T = V  dO^T     (A = V  smem K-major,  B = dO smem K-major)            -> TMEM DPT
 //   dV  += P^T  dO     (A = P^T  in TMEM,     B = dO smem MN-major)           -> TMEM DV
-//   dQ   = dS   K      (A = dS^T smem read MN-major, B = K smem MN-major)     -> TMEM DPT (aliases dP^T)
-//   dK  += dS^T Q      (A = dS^T smem K-major, B = Q  smem MN-major)          -> TMEM DK
+//   dK  += dS^T Q      (A = dS^T in TMEM,     B = Q  smem MN-major)           -> TMEM DK
+//   dQ   = dS   K      (A = dS^T smem read MN-major, B = K smem MN-major)     -> TMEM DPT (aliases dP^T/dS^T)
 // TMEM columns: ST [0,128)  DPT [128,256)  DV [256,256+D)  DK [256+D,256+2D).
 // Two independent MMA issue streams, one warp each, interleaved by the tensor pipe:
 //   stream X (owns the ST columns):   S^T(0) ; for each tile i:  [P(i) ready] dV(i) . S^T(i+1)
-//   stream Y (owns the DPT columns):  for each tile i:  [dQ(i-1) drained] dP^T(i) ; [dS(i) ready] dQ(i) . dK(i)
+//   stream Y (owns the DPT columns):  for each tile i:  [dQ(i-1) drained] dP^T(i) ; [dS(i) ready] dK(i) . dQ(i)
 // so neither chain waits for the other's softmax phase (a single in-order issuer made dP^T(i) queue behind dV(i)).
 //
 // Warps: 0-3 / 4-7 compute warpgroups (thread = kv row; WG0 takes query columns 0-63, WG1 64-127),
@@ -33,9 +33,12 @@
 #define FA_BWD_TRACE_EVENTS 16
 __device__ long long fa_bwd_trace_buf[FA_BWD_TRACE_EVENTS * FA_BWD_TRACE_ITERS];
 __device__ int fa_bwd_trace_block = 0;
+__device__ __forceinline__ int fa_bwd_lin_block() {
+  return static_cast<int>(blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z));
+}
 #define FA_TRACE(ev, it)                                                                       \
   do {                                                                                         \
-    if (static_cast<int>(blockIdx.x) == fa_bwd_trace_block && (it) < FA_BWD_TRACE_ITERS)       \
+    if (fa_bwd_lin_block() == fa_bwd_trace_block && (it) < FA_BWD_TRACE_ITERS)                 \
       fa_bwd_trace_buf[(ev) * FA_BWD_TRACE_ITERS + (it)] = clock64();                          \
   } while (0)
 #else
@@ -46,12 +49,13 @@ namespace fa {
 
 struct BwdParams {
   const float* rowstats;  // (bh, nqt, 2, 128): -lse*log2e then -delta, per 128-row query tile
-  int n_q, n_kv, bh, causal, diag, nqt, nkt;
+  int n_q, n_kv, bh, causal, diag, nqt, nkt, group_log2;
   float scale_log2, scale;
 };
 
 constexpr int kBwdThreads = 480;  // 15 warps (16 x 128 registers does not launch: the register file has no slack)
 constexpr int kT = 128;  // tile edge (query rows and kv rows)
+constexpr int kRankBitsY = 15;  // grid.y carries up to 2^15 kv tiles
 
 template <int D>
 struct BwdCfg {
@@ -76,7 +80,7 @@ static_assert(BwdCfg<128>::kSmemBytes <= 232448, "backward smem budget");
 
 enum BwdBar : int {
   kBarKV = 0, kBarQFull0, kBarQFull1, kBarQEmpty0, kBarQEmpty1, kBarDOFull0, kBarDOFull1, kBarDOEmpty0, kBarDOEmpty1,
-  kBarSFull, kBarDPFull, kBarPReady, kBarDSReady, kBarDQFull, kBarDQDrained, kBarStageFree0, kBarStageFree1,
+  kBarSFull, kBarDPFull, kBarDPIssued, kBarPReady, kBarDSHalf, kBarDSReady, kBarDQFull, kBarDQDrained, kBarStageFree0, kBarStageFree1,
   kBarDKVDone, kBarCount
 };
 
@@ -103,8 +107,12 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
   const int warp = static_cast<int>(warp_uniform(threadIdx.x >> 5));
   const int lane = threadIdx.x & 31;
 
-  const int bh = blockIdx.x / p.nkt;
-  const int j = blockIdx.x % p.nkt;  // kv tile; ascending = heaviest first under the causal mask
+  // Work-item order through the grid shape (see work_item() in ptx.cuh; no division in the kernel): x = slice inside
+  // its group (fastest), y = kv tile j (ascending = heaviest first under the causal mask), z = slice group; tile
+  // indices beyond the y limit of a grid are folded into x above the slice bits.
+  const int j = static_cast<int>(((blockIdx.x >> p.group_log2) << kRankBitsY) + blockIdx.y);
+  const int bh = static_cast<int>((blockIdx.z << p.group_log2) + (blockIdx.x & ((1u << p.group_log2) - 1u)));
+  if (bh >= p.bh || j >= p.nkt) return;  // padding of the last group / folded tile indices
   int i_min = 0;
   if (p.causal) {
     const int first = j * kT - p.diag;  // first query row that sees this tile's first key
@@ -146,6 +154,9 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
 #ifndef FA_BWD_DK_FROM_SMEM
 #define FA_BWD_DK_FROM_SMEM 0  // 1: dQ issued before dK, dK reads dS^T from shared memory (measured: slower)
 #endif
+#ifndef FA_BWD_SPLIT_DS
+#define FA_BWD_SPLIT_DS 1  // dK's first half is issued as soon as the first half of every dS^T row is in TMEM
+#endif
 #ifndef FA_BWD_L2_AHEAD
 #define FA_BWD_L2_AHEAD 2  // tiles of L2 prefetch distance beyond the shared-memory ring
 #endif
@@ -160,7 +171,7 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
   if (warp == 12 && lane == 0) {
     for (int b = 0; b < kBarCount; ++b) {
       uint32_t count = 1u;
-      if (b == kBarPReady || b == kBarDSReady) count = 256u;
+      if (b == kBarPReady || b == kBarDSReady || b == kBarDSHalf) count = 256u;
       if (b == kBarDQDrained) count = 128u;
       // operands shared by both MMA streams are released by two commits
       if (b == kBarQEmpty0 || b == kBarQEmpty1 || b == kBarDOEmpty0 || b == kBarDOEmpty1 || b == kBarDKVDone)
@@ -225,7 +236,8 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
           }
         }
         if (clock64() - t0 > FA_WAIT_TIMEOUT_CYCLES) {
-          printf("fa_sm100 bwd: producer timeout (block %d, q_next %d, do_next %d of %d)\n", blockIdx.x, q_next, do_next,
+          printf("fa_sm100 bwd: producer timeout (block %d,%d,%d q_next %d, do_next %d of %d)\n", blockIdx.x, blockIdx.y,
+                 blockIdx.z, q_next, do_next,
                  n_iter);
           __trap();
         }
@@ -261,6 +273,15 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
         for (int kk = 0; kk < kT / 16; ++kk) {
           const uint32_t a = tmem_base + a_col + (kk < 4 ? kk * 8 : 64 + (kk - 4) * 8);
           umma_ts(tmem_base + d_col, a, umma_desc(b_lo + kk * 128), idesc_acc, (acc || kk > 0) ? 1u : 0u);
+        }
+      };
+      // same product restricted to the first (part 0) or second (part 1) 32 queries of each warpgroup's 64
+      auto mma_from_tmem_part = [&](uint32_t d_col, uint32_t a_col, uint32_t b_lo, bool acc, int part) {
+#pragma unroll
+        for (int x = 0; x < 4; ++x) {
+          const int kk = (x >> 1) * 4 + part * 2 + (x & 1);  // part 0: 0,1,4,5   part 1: 2,3,6,7
+          const uint32_t a = tmem_base + a_col + (kk < 4 ? kk * 8 : 64 + (kk - 4) * 8);
+          umma_ts(tmem_base + d_col, a, umma_desc(b_lo + kk * 128), idesc_acc, (acc || x > 0) ? 1u : 0u);
         }
       };
       // dQ[q, d] = dS[q, kv] . K[kv, d]   (contraction over the 128 kv rows; both operands MN-major)
@@ -299,6 +320,9 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
           const uint32_t st = it & 1;
           mbar_wait(&bars[kBarDOFull0 + st], (it >> 1) & 1);
           mbar_wait(&bars[kBarPReady], it & 1);
+          // dP^T(it) heads the loop that sets the iteration period (dP -> dS -> dK.dQ -> drain -> dP(next)): let stream Y
+          // put it into the tensor pipe first; dV(it) and S^T(it+1) have a whole iteration of slack
+          mbar_wait(&bars[kBarDPIssued], it & 1);
           tc_fence_after();
           if (lane == 0) FA_TRACE(0, it);
           if (elect_one()) {
@@ -331,9 +355,16 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
             mma_kmajor(kColDPT, v_km, do_km + st * kTileLo);  // dP^T(it) = V dO^T
             tc_commit(&bars[kBarDPFull]);
             tc_commit(&bars[kBarDOEmpty0 + st]);
+            mbar_arrive(&bars[kBarDPIssued]);
           }
           __syncwarp();
           mbar_wait(&bars[kBarQFull0 + st], (it >> 1) & 1);
+#if FA_BWD_SPLIT_DS && !FA_BWD_DK_FROM_SMEM
+          mbar_wait(&bars[kBarDSHalf], it & 1);
+          tc_fence_after();
+          if (elect_one()) mma_from_tmem_part(kColDK, kColDPT, q_mn + st * kTileLo, it > 0, 0);
+          __syncwarp();
+#endif
           mbar_wait(&bars[kBarDSReady], it & 1);
           tc_fence_after();
           if (lane == 0) FA_TRACE(3, it);
@@ -343,6 +374,11 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
             tc_commit(&bars[kBarDQFull]);
             mma_dk(q_mn + st * kTileLo, it > 0);            // dK(it) += dS^T Q
             tc_commit(&bars[kBarQEmpty0 + st]);
+#elif FA_BWD_SPLIT_DS
+            mma_from_tmem_part(kColDK, kColDPT, q_mn + st * kTileLo, true, 1);  // second half of dK(it) += dS^T Q
+            tc_commit(&bars[kBarQEmpty0 + st]);
+            mma_dq();                                                            // dQ(it) = dS K overwrites dS^T
+            tc_commit(&bars[kBarDQFull]);
 #else
             mma_from_tmem(kColDK, kColDPT, q_mn + st * kTileLo, it > 0);  // dK(it) += dS^T Q (reads dS^T before ...
             tc_commit(&bars[kBarQEmpty0 + st]);
@@ -437,7 +473,7 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
       }
       if constexpr (!Cfg::kStageInDO) named_bar_sync(3, 128);  // dedicated staging is reused by the very next tile
     }
-    if (row == 0) tma_store_wait_all<0>();
+    if (row == 0) tma_store_wait_exit();  // staging read; the reduce itself completes by grid end
   } else if (warp < 8) {
     // ===================================== compute warpgroups =====================================
     const int wg = warp >> 2;
@@ -464,7 +500,7 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
       tc_fence_after();
       if (threadIdx.x == 0) FA_TRACE(4, it);
 #ifdef FA_BWD_TRACE
-      if (threadIdx.x == 0 && static_cast<int>(blockIdx.x) == fa_bwd_trace_block && it < FA_BWD_TRACE_ITERS) {
+      if (threadIdx.x == 0 && fa_bwd_lin_block() == fa_bwd_trace_block && it < FA_BWD_TRACE_ITERS) {
         long long gt;  // wall-clock ns next to the cycle stamp: calibrates the SM clock under load
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
         fa_bwd_trace_buf[15 * FA_BWD_TRACE_ITERS + it] = gt;
@@ -534,6 +570,13 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
           if (c + 1 < 4) tc_wait_ld();
 #if !FA_BWD_DK_FROM_SMEM
           tmem_st8(t_dpt + c * 8, pk);  // packed dS^T over the dP^T columns this thread has already consumed
+#if FA_BWD_SPLIT_DS
+          if (c == 1) {  // first 32 queries of this warpgroup are in TMEM: dK can start on them
+            tc_wait_st();
+            tc_fence_before();
+            mbar_arrive(&bars[kBarDSHalf]);
+          }
+#endif
 #endif
         }
       }
@@ -583,7 +626,7 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
       const CUtensorMap* tm = wg == 0 ? &tm_dv : &tm_dk;
       for (int ch = 0; ch < kChunks; ++ch) tma_store_3d(tm, stage_tile + ch * kSub, ch * 64, j * kT, bh);
       tma_store_commit();
-      tma_store_wait_all<0>();
+      tma_store_wait_exit();  // K/V staging has been read; the stores complete by grid end
     }
   }
 
@@ -665,6 +708,8 @@ static int launch_bwd(const Geometry& g, const void* q, const void* k, const voi
   p.diag = g.diag;
   p.nqt = static_cast<int>((g.n_q + kT - 1) / kT);
   p.nkt = static_cast<int>((g.n_kv + kT - 1) / kT);
+  p.group_log2 = sched_group_log2(g.causal != 0, p.nkt, g.bh, false);
+  while (((g.bh + (1ll << p.group_log2) - 1) >> p.group_log2) > 65535) ++p.group_log2;  // grid.z limit
   p.scale = g.scale;
   p.scale_log2 = g.scale * 1.4426950408889634f;
 
@@ -677,10 +722,12 @@ static int launch_bwd(const Geometry& g, const void* q, const void* k, const voi
       return FA_SM100_ELAUNCH;
     if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
-  const long long nblocks = static_cast<long long>(p.nkt) * g.bh;
-  if (nblocks > 0x7fffffffll) return FA_SM100_EINVAL_SHAPE;
-  kern<<<static_cast<unsigned>(nblocks), kBwdThreads, Cfg::kSmemBytes, stream>>>(tm_q, tm_k, tm_v, tm_do, tm_dq,
-                                                                                tm_dk, tm_dv, p);
+  const long long rank_lo = p.nkt < (1 << kRankBitsY) ? p.nkt : (1 << kRankBitsY);
+  const long long rank_hi = (p.nkt + (1 << kRankBitsY) - 1) >> kRankBitsY;
+  const long long gx = rank_hi << p.group_log2, gz = (g.bh + (1ll << p.group_log2) - 1) >> p.group_log2;
+  if (gx > 0x7fffffffll || gz > 65535) return FA_SM100_EINVAL_SHAPE;
+  const dim3 grid(static_cast<unsigned>(gx), static_cast<unsigned>(rank_lo), static_cast<unsigned>(gz));
+  kern<<<grid, kBwdThreads, Cfg::kSmemBytes, stream>>>(tm_q, tm_k, tm_v, tm_do, tm_dq, tm_dk, tm_dv, p);
   return launch_status();
 }
 

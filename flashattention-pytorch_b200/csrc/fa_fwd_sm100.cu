@@ -28,7 +28,7 @@ struct FwdParams {
   const float* lse_prev;
   long long lse_bh_stride;
   long long o_bh_stride;  // elements; o_prev shares o's geometry
-  int n_q, n_kv, bh, causal, diag, npairs;
+  int n_q, n_kv, bh, causal, diag, npairs, group_log2;
   float scale_log2;  // softmax_scale * log2(e)
 };
 
@@ -63,6 +63,26 @@ __device__ __forceinline__ int fwd_num_steps(int row0, const FwdParams& p) {
   return n;
 }
 
+constexpr int kRankBitsY = 15;  // grid.y carries up to 2^15 tile ranks
+// Optional per-CTA lifetime trace (build with -DFA_FWD_TRACE; tools/fwd_trace.py): SM id, wall-clock entry/exit and the
+// cycle stamps of the prologue / main loop / epilogue boundaries of every CTA, to size the fixed cost per work item.
+#ifdef FA_FWD_TRACE
+#define FA_FWD_TRACE_MAX_CTAS 8192
+__device__ long long fa_fwd_trace_buf[FA_FWD_TRACE_MAX_CTAS * 10];
+__device__ __forceinline__ long long fa_globaltimer() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define FA_FWD_STAMP(slot, value)                                                                     \
+  do {                                                                                                \
+    const unsigned lin_ = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);             \
+    if (lin_ < FA_FWD_TRACE_MAX_CTAS) fa_fwd_trace_buf[lin_ * 10 + (slot)] = (value);                 \
+  } while (0)
+#else
+#define FA_FWD_STAMP(slot, value) do { } while (0)
+#endif
+
 template <int D, bool kBF16>
 __global__ void __launch_bounds__(kFwdThreads, 1)
 fa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
@@ -90,10 +110,24 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
 
   const int warp = static_cast<int>(warp_uniform(threadIdx.x >> 5));
   const int lane = threadIdx.x & 31;
+#ifdef FA_FWD_TRACE
+  if (threadIdx.x == 0) {
+    uint32_t smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    FA_FWD_STAMP(0, static_cast<long long>(smid));
+    FA_FWD_STAMP(1, fa_globaltimer());
+    FA_FWD_STAMP(2, clock64());
+  }
+#endif
 
-  // heavy (late, for causal) tile pairs first; all pairs of one slice adjacent so its K/V stay L2-resident
-  const int bh = blockIdx.x / p.npairs;
-  const int pair = p.npairs - 1 - (blockIdx.x % p.npairs);
+  // heavy (late, for causal) tile pairs first, over groups of slices small enough for their K/V to stay L2-resident
+  // Work-item order (see work_item() in ptx.cuh for the idea), expressed through the grid shape so that the kernel
+  // needs no division: x = slice inside its group (fastest), y = tile-pair rank (heaviest first), z = slice group.
+  // Ranks beyond the y limit of a grid are folded into x above the slice bits.
+  const uint32_t rank = ((blockIdx.x >> p.group_log2) << kRankBitsY) + blockIdx.y;
+  const int bh = static_cast<int>((blockIdx.z << p.group_log2) + (blockIdx.x & ((1u << p.group_log2) - 1u)));
+  if (bh >= p.bh || rank >= static_cast<uint32_t>(p.npairs)) return;  // padding of the last group / folded ranks
+  const int pair = p.npairs - 1 - static_cast<int>(rank);
   const int row0_t0 = pair * 2 * kBM;
   const int nt0 = fwd_num_steps(row0_t0, p);
   const int nt1 = fwd_num_steps(row0_t0 + kBM, p);
@@ -138,6 +172,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = warp_uniform(*tmem_slot);
+  if (threadIdx.x == 0) FA_FWD_STAMP(3, clock64());  // prologue done (barriers, TMEM, first loads issued)
 
   if (warp == 8) {
     // ===================================== TMA producer =====================================
@@ -259,6 +294,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
       const uint32_t t_sb = t_s + buf * kStep;
       mbar_wait(&s_full[wg * 2 + buf], (j >> 1) & 1);
       tc_fence_after();
+      if (threadIdx.x == 0 && j == 0) FA_FWD_STAMP(4, clock64());  // first scores have arrived
       float s[kStep];
       tmem_ld32(t_sb, reinterpret_cast<uint32_t*>(s));
       tmem_ld32(t_sb + 32, reinterpret_cast<uint32_t*>(s) + 32);
@@ -341,6 +377,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
     }
 
     // ------------------------------- epilogue: O / l, lse, optional LSE merge, TMA store -------------------------------
+    if (threadIdx.x == 0) FA_FWD_STAMP(5, clock64());  // last softmax step handed over
     if (nt > 0) {
       if (nt > 1) mbar_wait(&pv_done[wg * 2 + ((nt - 2) & 1)], ((nt - 2) >> 1) & 1);
       mbar_wait(&pv_done[wg * 2 + ((nt - 1) & 1)], ((nt - 1) >> 1) & 1);
@@ -348,6 +385,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
     } else {
       mbar_wait(&q_full[wg], 0);  // the Q buffer doubles as the O staging tile: its TMA load must have landed
     }
+    if (threadIdx.x == 0) FA_FWD_STAMP(6, clock64());  // last PV finished
     const bool has_mass = l_sum > 0.f;
     float w_cur = has_mass ? 1.f / l_sum : 0.f;
     const float m_fin = (m_ref == -INFINITY) ? 0.f : m_ref;
@@ -410,13 +448,20 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
     if (row == 0 && tile_row0 < p.n_q) {
       for (int ch = 0; ch < kChunks; ++ch) tma_store_3d(&tm_o, stage_tile + ch * kSub, ch * 64, tile_row0, bh);
       tma_store_commit();
-      tma_store_wait_all<0>();
+      tma_store_wait_exit();  // the staging tile has been read; the stores themselves complete by grid end
     }
+    if (threadIdx.x == 0) FA_FWD_STAMP(7, clock64());  // tile 0 stored
   }
 
   tc_fence_before();
   __syncthreads();
   if (warp == 9) tmem_dealloc(tmem_base, 512);
+#ifdef FA_FWD_TRACE
+  if (threadIdx.x == 0) {
+    FA_FWD_STAMP(8, clock64());
+    FA_FWD_STAMP(9, fa_globaltimer());
+  }
+#endif
 }
 
 template <int D, bool kBF16>
@@ -443,6 +488,8 @@ static int launch_fwd(const Geometry& g, const void* q, const void* k, const voi
   p.causal = g.causal;
   p.diag = g.diag;
   p.npairs = static_cast<int>((g.n_q + 2 * kBM - 1) / (2 * kBM));
+  p.group_log2 = sched_group_log2(g.causal != 0, p.npairs, g.bh, false);
+  while (((g.bh + (1ll << p.group_log2) - 1) >> p.group_log2) > 65535) ++p.group_log2;  // grid.z limit
   p.scale_log2 = g.scale * 1.4426950408889634f;
 
   auto kern = fa_fwd_kernel<D, kBF16>;
@@ -454,9 +501,12 @@ static int launch_fwd(const Geometry& g, const void* q, const void* k, const voi
       return FA_SM100_ELAUNCH;
     if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
-  const long long nblocks = static_cast<long long>(p.npairs) * g.bh;
-  if (nblocks > 0x7fffffffll) return FA_SM100_EINVAL_SHAPE;
-  kern<<<static_cast<unsigned>(nblocks), kFwdThreads, Cfg::kSmemBytes, stream>>>(tm_q, tm_k, tm_v, tm_o, p);
+  const long long rank_lo = p.npairs < (1 << kRankBitsY) ? p.npairs : (1 << kRankBitsY);
+  const long long rank_hi = (p.npairs + (1 << kRankBitsY) - 1) >> kRankBitsY;
+  const long long gx = rank_hi << p.group_log2, gz = (g.bh + (1ll << p.group_log2) - 1) >> p.group_log2;
+  if (gx > 0x7fffffffll || gz > 65535) return FA_SM100_EINVAL_SHAPE;
+  const dim3 grid(static_cast<unsigned>(gx), static_cast<unsigned>(rank_lo), static_cast<unsigned>(gz));
+  kern<<<grid, kFwdThreads, Cfg::kSmemBytes, stream>>>(tm_q, tm_k, tm_v, tm_o, p);
   return launch_status();
 }
 
@@ -479,3 +529,11 @@ extern "C" int fa_sm100_fwd(const fa_sm100_shape* s, const void* q, const void* 
   return g.dtype == FA_SM100_DTYPE_BF16 ? fa::launch_fwd<64, true>(g, q, k, v, o, lse, o_prev, lse_prev, st)
                                         : fa::launch_fwd<64, false>(g, q, k, v, o, lse, o_prev, lse_prev, st);
 }
+
+#ifdef FA_FWD_TRACE
+// debug build only: copy the per-CTA lifetime stamps (10 values per CTA) of the last forward launch to the host
+extern "C" int fa_sm100_debug_fwd_trace(long long* host_dst, int n_ctas) {
+  if (!host_dst || n_ctas <= 0 || n_ctas > FA_FWD_TRACE_MAX_CTAS) return -1;
+  return cudaMemcpyFromSymbol(host_dst, fa::fa_fwd_trace_buf, sizeof(long long) * 10 * n_ctas) == cudaSuccess ? n_ctas : -1;
+}
+#endif

@@ -34,6 +34,15 @@ __device__ __forceinline__ bool elect_one() {
 }
 __device__ __forceinline__ uint32_t warp_uniform(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
 
+// Work-item order for grids whose items differ in cost (causal masks), used by the forward and backward kernels:
+// slices are taken in groups of 2^group_log2; inside a group the heaviest tile rank of every slice comes first, then
+// the next rank, ... (longest-processing-time-first, so the grid's tail is made of the cheapest items), while a group
+// stays small enough for its K/V (or Q/dO) to live in L2.  group_log2 == 0 is plain slice-major order.
+// The order is expressed through the GRID SHAPE -- x = slice inside its group, y = tile rank, z = group; blocks are
+// dispatched x-fastest -- so the kernels read it off blockIdx with shifts and masks.  Computing the same thing from a
+// 1-D block index (one or two divisions) kept the index arithmetic, and every TMA coordinate and MMA-loop trip count
+// derived from it, out of the uniform datapath and cost the forward 7-10% (measured, round 1).
+
 // Hang guard: a blocked barrier wait traps after ~4 s instead of wedging the GPU.
 #ifndef FA_WAIT_TIMEOUT_CYCLES
 #define FA_WAIT_TIMEOUT_CYCLES (8000000000ll)
@@ -153,6 +162,18 @@ __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk
 template <int N>
 __device__ __forceinline__ void tma_store_wait_read() {
   asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+// before a CTA exits only its shared-memory sources must have been read (the writes complete by grid end);
+// -DFA_EXIT_WAIT_ALL=1 waits for full completion instead (A/B knob)
+#ifndef FA_EXIT_WAIT_ALL
+#define FA_EXIT_WAIT_ALL 0
+#endif
+__device__ __forceinline__ void tma_store_wait_exit() {
+#if FA_EXIT_WAIT_ALL
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+#else
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+#endif
 }
 template <int N>
 __device__ __forceinline__ void tma_store_wait_all() {

@@ -38,7 +38,14 @@ def main():
         ext.bwd_raw(q, k, v, o, do, lse, causal, d ** -0.5)
     torch.cuda.synchronize()
     nkt = n // 128
-    block = (bh // 2) * nkt + (0 if causal else nkt // 2)  # a middle slice; the heaviest kv tile when causal
+    # a middle slice; the heaviest kv tile when causal.  Linear block id of (slice, kv tile) under the library's grid
+    # shape: x = slice inside its group, y = kv tile, z = group (csrc/fa_host.cuh sched_group_log2)
+    lg = 0
+    if causal:
+        while (2 << lg) <= max(1, 296 // nkt) and (2 << lg) <= bh:
+            lg += 1
+    sl, jt = bh // 2, (0 if causal else nkt // 2)
+    block = (sl & ((1 << lg) - 1)) + (1 << lg) * (jt + nkt * (sl >> lg))
     assert fn(block, None, 0) == 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()

@@ -51,6 +51,9 @@ def perf():
         o, lse = ext.fwd_raw(q, k, v, causal, d ** -0.5)
         flops_f = 4.0 * bh * n * n * d * (0.5 if causal else 1.0)
         t_f = time_ms(lambda: ext.fwd_raw(q, k, v, causal, d ** -0.5))
+        if "--fwd-only" in sys.argv:
+            print(f"bh={bh} n={n} causal={int(causal)}: fwd {t_f:.3f} ms {flops_f / t_f / 1e9:7.1f} TFLOP/s", flush=True)
+            continue
         t_b = time_ms(lambda: ext.bwd_raw(q, k, v, o, do, lse, causal, d ** -0.5))
         print(f"bh={bh} n={n} causal={int(causal)}: fwd {t_f:.3f} ms {flops_f / t_f / 1e9:7.1f} TFLOP/s | "
               f"bwd(all launches) {t_b:.3f} ms {2.5 * flops_f / t_b / 1e9:7.1f} TFLOP/s | "
