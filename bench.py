@@ -65,17 +65,39 @@ def measured_peaks():
 # ----------------------------------------------------------------------------------------------------------------------
 # clocks sampling (nvidia-smi during the timed region)
 # ----------------------------------------------------------------------------------------------------------------------
+_NVML_SAMPLER_SRC = r"""
+import sys, time
+import pynvml as n
+n.nvmlInit()
+h = n.nvmlDeviceGetHandleByIndex(int(sys.argv[1]))
+smax = n.nvmlDeviceGetMaxClockInfo(h, n.NVML_CLOCK_SM)
+reasons = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or n.nvmlDeviceGetCurrentClocksThrottleReasons
+out = open(sys.argv[2], "w", buffering=1)
+out.write("ready %f\n" % time.time())
+while True:
+    try:
+        sm = n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM)
+        pw = n.nvmlDeviceGetPowerUsage(h) / 1000.0
+        mask = int(reasons(h))
+        out.write("%f %d %d %.3f %d\n" % (time.time(), sm, smax, pw, mask))
+    except Exception:
+        pass
+    time.sleep(0.001)
+"""
+
+
 class ClockSampler:
-    """SM clock / power / throttle reasons sampled DURING the timed region.  NVML in a thread (a sample every ~2 ms, so
-    even a 20 ms region gets several); `nvidia-smi -lms` as the fallback when the NVML bindings are unusable."""
+    """SM clock / power / throttle reasons sampled DURING the timed region by a separate process polling NVML every
+    ~1-3 ms (its own interpreter: the bench's launch loop cannot starve it), so even a 20 ms region gets several
+    samples; `nvidia-smi -lms` is the fallback when the NVML bindings are unusable."""
     FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
               "clocks_event_reasons.sw_power_cap")
     NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+    BITS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
     def __init__(self, index: int):
-        self.index, self.rows, self.proc, self.thread = index, [], None, None
-        self.nvml, self.handle, self.stop_flag, self.sm_max = None, None, threading.Event(), None
+        self.index, self.rows, self.proc, self.thread, self.path, self.mode = index, [], None, None, None, None
 
     def _physical_index(self):
         vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
@@ -86,59 +108,60 @@ class ClockSampler:
 
     def start(self):
         try:
-            import pynvml
-            pynvml.nvmlInit()
-            self.handle = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index())
-            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
-            self.nvml = pynvml
-            self.thread = threading.Thread(target=self._poll_nvml, daemon=True)
-            self.thread.start()
-            return
+            import pynvml  # noqa: F401  (only to know the child can import it)
+            import tempfile
+            fd, self.path = tempfile.mkstemp(prefix="fa_clocks_", suffix=".txt")
+            os.close(fd)
+            self.proc = subprocess.Popen([sys.executable, "-c", _NVML_SAMPLER_SRC, str(self._physical_index()), self.path],
+                                         stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+            t_end = time.time() + 5.0
+            while time.time() < t_end:  # wait until the child has initialised NVML and started polling
+                if os.path.getsize(self.path) > 0:
+                    self.mode = "nvml"
+                    return
+                if self.proc.poll() is not None:
+                    break
+                time.sleep(0.01)
+            self.proc.kill()
         except Exception:  # noqa: BLE001
-            self.nvml = None
+            pass
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
                                           "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
         except OSError:
+            self.proc = None
             return
+        self.mode = "nvidia-smi"
         self.thread = threading.Thread(target=self._read, daemon=True)
         self.thread.start()
-
-    def _poll_nvml(self):
-        n = self.nvml
-        bits = {"hw_slowdown": getattr(n, "nvmlClocksEventReasonHwSlowdown", 0x8),
-                "hw_thermal_slowdown": getattr(n, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
-                "sw_thermal_slowdown": getattr(n, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
-                "sw_power_cap": getattr(n, "nvmlClocksEventReasonSwPowerCap", 0x4)}
-        reasons_fn = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
-            getattr(n, "nvmlDeviceGetCurrentClocksThrottleReasons")
-        while not self.stop_flag.is_set():
-            try:
-                sm = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
-                pw = n.nvmlDeviceGetPowerUsage(self.handle) / 1000.0
-                mask = int(reasons_fn(self.handle))
-                flags = ["Active" if mask & bits[k] else "Not Active" for k in self.NAMES]
-                self.rows.append((time.time(), [str(sm), str(self.sm_max), str(pw), *flags]))
-            except Exception:  # noqa: BLE001
-                pass
-            time.sleep(0.002)
 
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
 
     def stop(self, t0, t1):
-        if self.nvml is not None:
-            self.stop_flag.set()
-            self.thread.join(timeout=1.0)
-            source, pad = "nvml", 0.0
-        elif self.proc is not None:
+        if self.proc is None:
+            return None
+        if self.mode == "nvml":
+            time.sleep(0.01)
+            self.proc.kill()
+            self.proc.wait()
+            pad = 0.0
+            try:
+                for line in open(self.path):
+                    f = line.split()
+                    if len(f) == 5:
+                        mask = int(f[4])
+                        flags = ["Active" if mask & self.BITS[k] else "Not Active" for k in self.NAMES]
+                        self.rows.append((float(f[0]), [f[1], f[2], f[3], *flags]))
+                os.unlink(self.path)
+            except OSError:
+                pass
+        else:
             time.sleep(0.15)
             self.proc.terminate()
-            source, pad = "nvidia-smi", 0.2
-        else:
-            return None
+            pad = 0.2
         inside = [r for ts, r in self.rows if t0 <= ts <= t1 + pad]
         rows = inside or [r for _, r in self.rows]
         if not rows:
@@ -147,7 +170,7 @@ class ClockSampler:
         reasons = sorted({n for r in rows for n, v in zip(self.NAMES, r[3:7]) if v.lower().startswith("active")})
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": float(rows[0][1]),
                 "power_w_max": max(float(r[2]) for r in rows), "samples": len(rows),
-                "samples_inside_timed_region": len(inside), "source": source, "reasons": reasons}
+                "samples_inside_timed_region": len(inside), "source": self.mode, "reasons": reasons}
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -449,6 +472,19 @@ def run_ours(args, workload, name):
     t_wall1 = time.time()
     ms_total = e0.elapsed_time(e1)
     clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+    if world == 1 and (clocks is None or not clocks.get("samples_inside_timed_region")):
+        # the region was too short for the sampler (or it started late): sample again over >= 0.2 s of the same steps
+        extra = ClockSampler(local)
+        extra.start()
+        tx0 = time.time()
+        while time.time() - tx0 < 0.2:
+            for _ in range(args.steps):
+                run_step()
+            torch.cuda.synchronize()
+        again = extra.stop(tx0, time.time())
+        if again is not None:
+            again["note"] = "sampled over extra replays of the same steps right after the timed region"
+            clocks = again
     t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

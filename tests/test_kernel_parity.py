@@ -174,3 +174,56 @@ def test_many_small_slices():
     o_r, lse_r = dense_forward(q[sl].cpu(), k[sl].cpu(), v[sl].cpu(), True, 0.125)
     assert error_report(o[sl], o_r, 5e-2, 5e-2)["violations"] == 0
     assert error_report(lse[sl], lse_r, 1e-3, 1e-3)["violations"] == 0
+
+
+@pytest.mark.parametrize("bh", [1, 3, 5, 7, 12])
+def test_causal_work_order_covers_every_slice(bh):
+    """The causal grids walk slices in power-of-two groups (heaviest tiles first); slice counts that are not a
+    multiple of the group size leave padding CTAs that must do nothing, and every real (slice, tile) must be done
+    exactly once: each slice has to match the same slice computed alone (bit-exact forward and dK/dV, dQ to fp32
+    reduction order)."""
+    torch.manual_seed(bh)
+    n, d = 640, 128
+    q, k, v, do = (torch.randn(bh, n, d, device="cuda", dtype=torch.bfloat16) for _ in range(4))
+    o, lse = ext.fwd_raw(q, k, v, True, d ** -0.5)
+    dq, dk, dv = ext.bwd_raw(q, k, v, o, do, lse, True, d ** -0.5)
+    for s in range(bh):
+        sl = slice(s, s + 1)
+        o1, lse1 = ext.fwd_raw(q[sl].contiguous(), k[sl].contiguous(), v[sl].contiguous(), True, d ** -0.5)
+        dq1, dk1, dv1 = ext.bwd_raw(q[sl].contiguous(), k[sl].contiguous(), v[sl].contiguous(), o1,
+                                    do[sl].contiguous(), lse1, True, d ** -0.5)
+        assert torch.equal(o1, o[sl]) and torch.equal(lse1, lse[sl])
+        assert torch.equal(dk1, dk[sl]) and torch.equal(dv1, dv[sl])
+        assert torch.allclose(dq1.float(), dq[sl].float(), rtol=1e-2, atol=1e-2)  # one 16-bit ulp at most
+
+
+@pytest.mark.parametrize("mode,dtype", [(4, torch.bfloat16), (4, torch.float16), (5, torch.bfloat16), (5, torch.float16)])
+def test_cta_pair_umma_probe(mode, dtype):
+    """cta_group::2 bring-up: one M=256 product across a CTA pair (mode 4: SS with B rows split across the pair,
+    mode 5: A from TMEM with B columns split) against torch.matmul."""
+    torch.manual_seed(mode)
+    a = torch.randn(256, 128, device="cuda", dtype=dtype)
+    b = torch.randn(128, 128, device="cuda", dtype=dtype)
+    out = ext.probe_umma(mode, a, b)
+    want = a.float() @ (b.float().T if mode == 4 else b.float())
+    assert (out - want).abs().max() < 1e-3
+
+
+def test_reduce_rate_probe_accumulates_exactly():
+    """The L2 reduce-add probe adds 1.0 per (kv tile, element): integers in fp32 are exact, so any lost or doubled
+    reduce shows up as a wrong count — for the TMA path and for the register (red.global.v4) path."""
+    acc = torch.zeros(3, 4 * 128, 128, device="cuda", dtype=torch.float32)
+    ext.probe_reduce_rate(acc, 5, 0)
+    ext.probe_reduce_rate(acc, 5, 1)
+    ext.probe_reduce_rate(acc, 5, 2)
+    ext.probe_reduce_rate(acc, 5, 7)
+    torch.cuda.synchronize()
+    assert bool((acc == 20.0).all())
+
+
+def test_mma_rate_probe_runs():
+    for pair, ts, n in ((0, 0, 64), (0, 1, 128), (1, 0, 128), (1, 1, 128), (1, 0, 256)):
+        ext.probe_mma_rate(pair, ts, n, 16, 4)
+    torch.cuda.synchronize()
+    with pytest.raises(RuntimeError):
+        ext.probe_mma_rate(1, 0, 128, 16, 3)  # a CTA pair needs an even CTA count
