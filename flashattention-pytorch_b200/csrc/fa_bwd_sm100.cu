@@ -41,8 +41,22 @@ __device__ __forceinline__ int fa_bwd_lin_block() {
     if (fa_bwd_lin_block() == fa_bwd_trace_block && (it) < FA_BWD_TRACE_ITERS)                 \
       fa_bwd_trace_buf[(ev) * FA_BWD_TRACE_ITERS + (it)] = clock64();                          \
   } while (0)
+// per-CTA lifetime stamps of EVERY CTA (8 values each): SM id, wall-clock entry/exit, cycle stamps of the boundaries
+#define FA_BWD_LIFE_MAX_CTAS 16384
+__device__ long long fa_bwd_life_buf[FA_BWD_LIFE_MAX_CTAS * 8];
+__device__ __forceinline__ long long fa_bwd_globaltimer() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define FA_LIFE(slot, value)                                                                   \
+  do {                                                                                         \
+    const int lin_ = fa_bwd_lin_block();                                                       \
+    if (lin_ < FA_BWD_LIFE_MAX_CTAS) fa_bwd_life_buf[lin_ * 8 + (slot)] = (value);             \
+  } while (0)
 #else
 #define FA_TRACE(ev, it) do { } while (0)
+#define FA_LIFE(slot, value) do { } while (0)
 #endif
 
 namespace fa {
@@ -113,6 +127,15 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
   const int j = static_cast<int>(((blockIdx.x >> p.group_log2) << kRankBitsY) + blockIdx.y);
   const int bh = static_cast<int>((blockIdx.z << p.group_log2) + (blockIdx.x & ((1u << p.group_log2) - 1u)));
   if (bh >= p.bh || j >= p.nkt) return;  // padding of the last group / folded tile indices
+#ifdef FA_BWD_TRACE
+  if (threadIdx.x == 0) {
+    uint32_t smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    FA_LIFE(0, static_cast<long long>(smid));
+    FA_LIFE(1, fa_bwd_globaltimer());
+    FA_LIFE(2, clock64());
+  }
+#endif
   int i_min = 0;
   if (p.causal) {
     const int first = j * kT - p.diag;  // first query row that sees this tile's first key
@@ -499,6 +522,7 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
       mbar_wait(&bars[kBarSFull], it & 1);
       tc_fence_after();
       if (threadIdx.x == 0) FA_TRACE(4, it);
+      if (threadIdx.x == 0 && it == 0) FA_LIFE(3, clock64());  // first scores have arrived
 #ifdef FA_BWD_TRACE
       if (threadIdx.x == 0 && fa_bwd_lin_block() == fa_bwd_trace_block && it < FA_BWD_TRACE_ITERS) {
         long long gt;  // wall-clock ns next to the cycle stamp: calibrates the SM clock under load
@@ -590,9 +614,11 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
     }
 
     // ------------------------------- epilogue: WG0 stores dV, WG1 stores dK * scale -------------------------------
+    if (threadIdx.x == 0) FA_LIFE(4, clock64());  // last dS handed over
     if (n_iter > 0) {
       mbar_wait(&bars[kBarDKVDone], 0);
       tc_fence_after();
+      if (threadIdx.x == 0) FA_LIFE(5, clock64());  // last dK/dV products finished
     } else {
       mbar_wait(&bars[kBarKV], 0);  // staging reuses the K/V tiles: their loads must have landed
     }
@@ -633,6 +659,12 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
   tc_fence_before();
   __syncthreads();
   if (warp == 13) tmem_dealloc(tmem_base, 512);
+#ifdef FA_BWD_TRACE
+  if (threadIdx.x == 0) {
+    FA_LIFE(6, clock64());
+    FA_LIFE(7, fa_bwd_globaltimer());
+  }
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -787,6 +819,10 @@ extern "C" int fa_sm100_bwd(const fa_sm100_shape* s, const void* q, const void* 
 
 #ifdef FA_BWD_TRACE
 // debug build only: select the CTA to trace / copy its timeline (events x FA_BWD_TRACE_ITERS clock64 values) to the host
+extern "C" int fa_sm100_debug_bwd_life(long long* host_dst, int n_ctas) {
+  if (!host_dst || n_ctas <= 0 || n_ctas > FA_BWD_LIFE_MAX_CTAS) return -1;
+  return cudaMemcpyFromSymbol(host_dst, fa_bwd_life_buf, sizeof(long long) * 8 * n_ctas) == cudaSuccess ? n_ctas : -1;
+}
 extern "C" int fa_sm100_debug_bwd_trace(int set_block, long long* host_dst, int max_values) {
   if (set_block >= 0) {
     long long zero[FA_BWD_TRACE_EVENTS * FA_BWD_TRACE_ITERS] = {};

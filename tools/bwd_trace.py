@@ -105,6 +105,40 @@ def main():
             print(f"  {name:55s} {val:8.0f} ns")
     else:
         gaps, period = {}, None
+    # ---- per-CTA lifetime of every CTA of the same launch ----
+    life_fn = getattr(lib, "fa_sm100_debug_bwd_life", None)
+    if life_fn is not None:
+        from collections import defaultdict
+        life_fn.restype = ctypes.c_int
+        life_fn.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        gsz = 1 << lg
+        n_ctas = min(16384, ((bh + gsz - 1) // gsz) * gsz * nkt)
+        lb = (ctypes.c_longlong * (8 * n_ctas))()
+        if life_fn(lb, n_ctas) == n_ctas:
+            rows = [[lb[c * 8 + x] for x in range(8)] for c in range(n_ctas)]
+            rows = [r for r in rows if r[7] > r[1] > 0]  # padding CTAs never stamp
+            k = sum(r[7] - r[1] for r in rows) / float(sum(r[6] - r[2] for r in rows))
+            t_first, t_last = min(r[1] for r in rows), max(r[7] for r in rows)
+            print(f"lifetime of {len(rows)} CTAs: span {(t_last - t_first) / 1000:.1f} us")
+            for name, (a, b) in (("prologue + first scores (entry -> S(0) ready)", (2, 3)),
+                                 ("main loop (S(0) -> last dS done)", (3, 4)),
+                                 ("tail (last dS -> last dK/dV product done)", (4, 5)),
+                                 ("epilogue + exit (convert, stage, TMA store, dealloc)", (5, 6))):
+                xs = [(r[b] - r[a]) * k for r in rows if r[b] > 0 and r[a] > 0]
+                print(f"  {name:55s} mean {sum(xs) / len(xs):8.0f} ns   min {min(xs):8.0f}   max {max(xs):8.0f}")
+            lifes = [r[7] - r[1] for r in rows]
+            print(f"  {'CTA lifetime (wall clock)':55s} mean {sum(lifes) / len(lifes):8.0f} ns")
+            by_sm = defaultdict(list)
+            for r in rows:
+                by_sm[r[0]].append((r[1], r[7]))
+            gaps, idle_tail = [], []
+            for lst in by_sm.values():
+                lst.sort()
+                gaps += [b0 - a1 for (a0, a1), (b0, b1) in zip(lst, lst[1:])]
+                idle_tail.append(t_last - lst[-1][1])
+            print(f"  {'gap between consecutive CTAs on one SM':55s} mean {sum(gaps) / max(len(gaps), 1):8.0f} ns")
+            print(f"  mean idle tail per SM {sum(idle_tail) / len(idle_tail) / 1000:.1f} us; "
+                  f"SM occupancy {100.0 * sum(lifes) / ((t_last - t_first) * len(by_sm)):.1f}%")
     out = ROOT / "gpurun_out"
     out.mkdir(exist_ok=True)
     tag = f"n{n}_c{int(causal)}"
