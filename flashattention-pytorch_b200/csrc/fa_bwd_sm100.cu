@@ -59,10 +59,18 @@ __device__ __forceinline__ long long fa_bwd_globaltimer() {
 #define FA_LIFE(slot, value) do { } while (0)
 #endif
 
+#ifndef FA_BWD_SPLIT_DRAIN
+#define FA_BWD_SPLIT_DRAIN 0  // d=128: the compute warpgroups reduce dQ columns 64-127 from registers (red.global.v4)
+                              // 1: for every query tile   2: only for a CTA's last tile   0: never.  Measured at C2:
+                              // 1 -> 689, 2 -> 903, 0 -> 915 TFLOP/s (the LSU reduce path is the slower one), so off
+#endif
+
 namespace fa {
 
 struct BwdParams {
   const float* rowstats;  // (bh, nqt, 2, 128): -lse*log2e then -delta, per 128-row query tile
+  float* dq_accum;        // fp32 dQ accumulator (bh, n_q, D) with slice stride dq_bh_stride (elements)
+  long long dq_bh_stride;
   int n_q, n_kv, bh, causal, diag, nqt, nkt, group_log2;
   float scale_log2, scale;
 };
@@ -107,6 +115,8 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
   using Cfg = BwdCfg<D>;
   constexpr int kSub = Cfg::kSub;
   constexpr int kChunks = D / 64;
+  constexpr int kSplitMode = D == 128 ? FA_BWD_SPLIT_DRAIN : 0;
+  constexpr bool kSplitDrain = kSplitMode == 1;  // compute warpgroups take part in every tile's drain
 
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* k_smem = smem + Cfg::kOffK;
@@ -195,7 +205,7 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
     for (int b = 0; b < kBarCount; ++b) {
       uint32_t count = 1u;
       if (b == kBarPReady || b == kBarDSReady || b == kBarDSHalf) count = 256u;
-      if (b == kBarDQDrained) count = 128u;
+      if (b == kBarDQDrained) count = kSplitDrain ? 384u : 128u;
       // operands shared by both MMA streams are released by two commits
       if (b == kBarQEmpty0 || b == kBarQEmpty1 || b == kBarDOEmpty0 || b == kBarDOEmpty1 || b == kBarDKVDone)
         count = 2u;
@@ -453,7 +463,8 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
       tc_wait_ld();
       stage_chunk(0, 0);
       stage_chunk(1, 32);
-      if constexpr (D == 128) {  // second 64 columns straight away: the accumulator goes back before any TMA bookkeeping
+      const bool split_now = kSplitMode == 1 || (kSplitMode == 2 && it == n_iter - 1);
+      if (D == 128 && !split_now) {  // second 64 columns straight away: TMEM goes back before any TMA bookkeeping
         tmem_ld32(tmem_base + lane_sel + kColDPT + 64, reinterpret_cast<uint32_t*>(v));
         tmem_ld32(tmem_base + lane_sel + kColDPT + 96, reinterpret_cast<uint32_t*>(v) + 32);
         tc_wait_ld();
@@ -467,7 +478,7 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
         reduce_chunk(0, 0);
         reduce_chunk(1, 32);
       }
-      if constexpr (D == 128) {
+      if (D == 128 && !split_now) {
         // columns 64-127 follow through the same two buffers, each as soon as its previous reduce has been read, so
         // the reduce engine (about 40 B/ns per SM, measured) never waits for the staging stores of a whole half
         if (row == 0) {
@@ -506,6 +517,50 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
     const uint32_t t_st = tmem_base + lane_sel + kColST + col_base;
     const uint32_t t_dpt = tmem_base + lane_sel + kColDPT + col_base;
     uint8_t* ds_row = ds_smem + wg * (kT * 128) + r * 128;
+
+    // d = 128: this warpgroup's share of the dQ(it) drain -- 32 of the columns 64-127, straight from TMEM to dq_accum
+    // with red.global.v4.  The compute warps idle for about a third of every iteration and TMEM lane r is query row
+    // r for dQ, so this halves what goes through the staging buffers and the TMA reduce (shared-memory port, the
+    // busiest unit of this kernel) and halves the drain left over when the CTA has nothing else to do.
+    // Lane pairs exchange halves so that each warp-wide red covers 16 rows x one full 32-byte sector.
+    auto drain_dq_share = [&](int it_prev) {
+      mbar_wait(&bars[kBarDQFull], it_prev & 1);
+      tc_fence_after();
+      const int q_row = tile_of(it_prev) * kT + r;
+      const bool odd = (lane & 1) != 0;
+      const int row_a = odd ? q_row - 1 : q_row;  // first red of a pair goes to the even lane's row ...
+      const int row_b = row_a + 1;                // ... the second to the odd lane's
+      float* base = p.dq_accum + static_cast<long long>(bh) * p.dq_bh_stride + 64 + wg * 32 + (odd ? 4 : 0);
+      float* pa = base + static_cast<long long>(row_a) * D;
+      float* pb = base + static_cast<long long>(row_b) * D;
+      const bool ok_a = row_a < p.n_q, ok_b = row_b < p.n_q;
+      const uint32_t t_dq = tmem_base + lane_sel + kColDPT + 64 + wg * 32;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        float v[16];
+        tmem_ld16(t_dq + h * 16, reinterpret_cast<uint32_t*>(v));
+        tc_wait_ld();
+        if (h == 1 && kSplitDrain) {
+          tc_fence_before();
+          mbar_arrive(&bars[kBarDQDrained]);
+        }
+#pragma unroll
+        for (int m = 0; m < 2; ++m) {
+          float x[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e)  // even lanes hand over their upper four values, odd lanes their lower four
+            x[e] = __shfl_xor_sync(0xffffffffu, odd ? v[8 * m + e] : v[8 * m + 4 + e], 1);
+          const int col = h * 16 + m * 8;
+          if (!odd) {
+            if (ok_a) red_add_v4(pa + col, v[8 * m], v[8 * m + 1], v[8 * m + 2], v[8 * m + 3]);
+            if (ok_b) red_add_v4(pb + col, x[0], x[1], x[2], x[3]);
+          } else {
+            if (ok_a) red_add_v4(pa + col, x[0], x[1], x[2], x[3]);
+            if (ok_b) red_add_v4(pb + col, v[8 * m + 4], v[8 * m + 5], v[8 * m + 6], v[8 * m + 7]);
+          }
+        }
+      }
+    };
 
     for (int it = 0; it < n_iter; ++it) {
       const int i = tile_of(it), st = it & 1;
@@ -559,6 +614,9 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
       tc_fence_before();
       mbar_arrive(&bars[kBarPReady]);
       if (threadIdx.x == 0) FA_TRACE(5, it);
+      if constexpr (kSplitDrain) {
+        if (it > 0) drain_dq_share(it - 1);  // must precede the dP^T(it) wait: dP^T(it) is issued once dQ(it-1) is out
+      }
 
       mbar_wait(&bars[kBarDPFull], it & 1);
       tc_fence_after();
@@ -613,6 +671,9 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
       if (threadIdx.x == 0) FA_TRACE(7, it);
     }
 
+    if constexpr (kSplitMode != 0) {
+      if (n_iter > 0) drain_dq_share(n_iter - 1);
+    }
     // ------------------------------- epilogue: WG0 stores dV, WG1 stores dK * scale -------------------------------
     if (threadIdx.x == 0) FA_LIFE(4, clock64());  // last dS handed over
     if (n_iter > 0) {
@@ -733,6 +794,8 @@ static int launch_bwd(const Geometry& g, const void* q, const void* k, const voi
 
   BwdParams p;
   p.rowstats = rowstats;
+  p.dq_accum = dq_accum;
+  p.dq_bh_stride = g.q_bh_stride;
   p.n_q = static_cast<int>(g.n_q);
   p.n_kv = static_cast<int>(g.n_kv);
   p.bh = static_cast<int>(g.bh);
