@@ -513,8 +513,9 @@ def run_ours(args, workload, name):
 
 
 def run_ring(args, workload, name):
-    """BASELINE C5: long-context causal ring attention, sequence zig-zag-sharded over the ranks, NCCL send/recv of the
-    K/V (and dK/dV) blocks overlapped with compute, partial outputs merged by LSE in the kernel epilogue."""
+    """BASELINE C5: long-context causal ring attention, sequence zig-zag-sharded over the ranks, K/V (and dK/dV) blocks
+    exchanged with the ring neighbours (symmetric-memory peer pulls by default, FA_RING_TRANSPORT=nccl for NCCL
+    send/recv) overlapped with compute, partial outputs merged by LSE in the kernel epilogue."""
     import torch.distributed as dist
 
     rank = int(os.environ.get("RANK", "0"))
@@ -569,6 +570,8 @@ def run_ring(args, workload, name):
     ms_step = float(t.item()) / args.steps
     clocks = sampler.stop(t0, t1) if rank == 0 else None
     value = (f_fwd + f_bwd) / (ms_step * 1e-3) / 1e12
+    transport = {"nccl": "NCCL P2P send/recv"}.get(os.environ.get("FA_RING_TRANSPORT", "auto"),
+                                                    "symmetric-memory peer pulls on the copy engines")
     if rank == 0:
         peaks = measured_peaks()
         kv_bytes = 2 * b * h * n_local * d * 2
@@ -577,7 +580,7 @@ def run_ring(args, workload, name):
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": name, "B": b, "H": h, "N_total": n, "N_per_gpu": n_local, "d": d, "causal": causal,
-                       "parallelism": f"ring attention x{world} (zig-zag sequence shards, NCCL P2P)",
+                       "parallelism": f"ring attention x{world} (zig-zag sequence shards, {transport})",
                        "nvlink_bytes_per_gpu_per_step": (world - 1) * kv_bytes + world * (kv_bytes + 2 * kv_bytes)},
             "frac_of_nominal_bf16_peak": value / world / NOMINAL_BF16_TFLOPS,
             "frac_of_measured_bf16_peak": value / world / peaks["burst"],
