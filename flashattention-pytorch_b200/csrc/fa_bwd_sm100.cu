@@ -190,15 +190,6 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
 #ifndef FA_BWD_SPLIT_DS
 #define FA_BWD_SPLIT_DS 1  // dK's first half is issued as soon as the first half of every dS^T row is in TMEM
 #endif
-#ifndef FA_BWD_L2_AHEAD
-#define FA_BWD_L2_AHEAD 2  // tiles of L2 prefetch distance beyond the shared-memory ring
-#endif
-  auto prefetch_q_tile = [&](int it) {
-    for (int c = 0; c < kChunks; ++c) tma_prefetch_l2_3d(&tm_q, c * 64, tile_of(it) * kT, bh);
-  };
-  auto prefetch_do_tile = [&](int it) {
-    for (int c = 0; c < kChunks; ++c) tma_prefetch_l2_3d(&tm_do, c * 64, tile_of(it) * kT, bh);
-  };
   // The producer lane initialises the barriers and starts K, V and the first two query tiles BEFORE the block-wide
   // sync, so their TMA latency overlaps the TMEM allocation and the rest of the prologue.
   if (warp == 12 && lane == 0) {
@@ -226,10 +217,6 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
       issue_q_tile(it);
       issue_do_tile(it);
     }
-    for (int it = 2; it < n_iter && it < 2 + FA_BWD_L2_AHEAD; ++it) {
-      prefetch_q_tile(it);
-      prefetch_do_tile(it);
-    }
   }
   if (warp == 13) {
     tmem_alloc(tmem_slot, 512);
@@ -253,7 +240,6 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
         if (q_next < n_iter && mbar_test_wait(&bars[kBarQEmpty0 + (q_next & 1)], ((q_next >> 1) & 1) ^ 1)) {
           issue_q_tile(q_next);
           FA_TRACE(12, q_next);
-          if (q_next + FA_BWD_L2_AHEAD < n_iter) prefetch_q_tile(q_next + FA_BWD_L2_AHEAD);
           ++q_next;
         }
         if (do_next < n_iter) {
@@ -264,7 +250,6 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
           if (ok) {
             issue_do_tile(do_next);
             FA_TRACE(13, do_next);
-            if (do_next + FA_BWD_L2_AHEAD < n_iter) prefetch_do_tile(do_next + FA_BWD_L2_AHEAD);
             ++do_next;
           }
         }
