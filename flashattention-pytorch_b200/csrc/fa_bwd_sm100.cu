@@ -77,7 +77,10 @@ struct BwdParams {
 
 constexpr int kBwdThreads = 480;  // 15 warps (16 x 128 registers does not launch: the register file has no slack)
 constexpr int kT = 128;  // tile edge (query rows and kv rows)
-constexpr int kRankBitsY = 15;  // grid.y carries up to 2^15 kv tiles
+#ifndef FA_GRID_Y_BITS
+#define FA_GRID_Y_BITS 15  // grid.y carries up to 2^15 kv tiles; larger indices fold into grid.x.  Tests build with 2 to
+#endif                     // exercise the folding at small sizes (tools/README.md)
+constexpr int kRankBitsY = FA_GRID_Y_BITS;
 
 template <int D>
 struct BwdCfg {

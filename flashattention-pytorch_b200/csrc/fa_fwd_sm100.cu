@@ -63,7 +63,10 @@ __device__ __forceinline__ int fwd_num_steps(int row0, const FwdParams& p) {
   return n;
 }
 
-constexpr int kRankBitsY = 15;  // grid.y carries up to 2^15 tile ranks
+#ifndef FA_GRID_Y_BITS
+#define FA_GRID_Y_BITS 15  // grid.y carries up to 2^15 tile ranks; larger indices fold into grid.x.  Tests build with 2 to
+#endif                     // exercise the folding at small sizes (tools/README.md)
+constexpr int kRankBitsY = FA_GRID_Y_BITS;
 // Optional per-CTA lifetime trace (build with -DFA_FWD_TRACE; tools/fwd_trace.py): SM id, wall-clock entry/exit and the
 // cycle stamps of the prologue / main loop / epilogue boundaries of every CTA, to size the fixed cost per work item.
 #ifdef FA_FWD_TRACE
