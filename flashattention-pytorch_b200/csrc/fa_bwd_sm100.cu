@@ -791,7 +791,7 @@ static int launch_bwd(const Geometry& g, const void* q, const void* k, const voi
   p.diag = g.diag;
   p.nqt = static_cast<int>((g.n_q + kT - 1) / kT);
   p.nkt = static_cast<int>((g.n_kv + kT - 1) / kT);
-  p.group_log2 = sched_group_log2(g.causal != 0, p.nkt, g.bh, false);
+  p.group_log2 = sched_group_log2(g.causal != 0, p.nkt, g.bh);
   while (((g.bh + (1ll << p.group_log2) - 1) >> p.group_log2) > 65535) ++p.group_log2;  // grid.z limit
   p.scale = g.scale;
   p.scale_log2 = g.scale * 1.4426950408889634f;

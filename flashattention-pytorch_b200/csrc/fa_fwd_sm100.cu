@@ -491,7 +491,7 @@ static int launch_fwd(const Geometry& g, const void* q, const void* k, const voi
   p.causal = g.causal;
   p.diag = g.diag;
   p.npairs = static_cast<int>((g.n_q + 2 * kBM - 1) / (2 * kBM));
-  p.group_log2 = sched_group_log2(g.causal != 0, p.npairs, g.bh, false);
+  p.group_log2 = sched_group_log2(g.causal != 0, p.npairs, g.bh);
   while (((g.bh + (1ll << p.group_log2) - 1) >> p.group_log2) > 65535) ++p.group_log2;  // grid.z limit
   p.scale_log2 = g.scale * 1.4426950408889634f;
 

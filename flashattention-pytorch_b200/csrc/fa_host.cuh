@@ -95,7 +95,7 @@ inline int check_device() {
 
 // log2 of the slices per scheduling group for cost-skewed (causal) grids: about two waves of CTAs per group (see
 // work_item()).  FA_SM100_SCHED_GROUP overrides the group size (tuning knob: 1 = slice-major order).
-inline int sched_group_log2(bool skewed, long long n_ranks, long long n_slices, bool must_divide) {
+inline int sched_group_log2(bool skewed, long long n_ranks, long long n_slices) {
   static int forced = [] {
     const char* e = std::getenv("FA_SM100_SCHED_GROUP");
     return e ? std::atoi(e) : 0;
@@ -105,8 +105,6 @@ inline int sched_group_log2(bool skewed, long long n_ranks, long long n_slices, 
   else if (skewed) g = (2 * 148) / (n_ranks > 0 ? n_ranks : 1);
   int lg = 0;
   while ((2ll << lg) <= g && (2ll << lg) <= n_slices) ++lg;  // largest power of two <= min(g, n_slices)
-  if (must_divide)
-    while (lg > 0 && (n_slices & ((1ll << lg) - 1))) --lg;  // ... that also divides the slice count (no padding CTAs)
   return lg;
 }
 inline int launch_status() { return cudaGetLastError() == cudaSuccess ? FA_SM100_OK : FA_SM100_ELAUNCH; }
