@@ -59,12 +59,6 @@ __device__ __forceinline__ long long fa_bwd_globaltimer() {
 #define FA_LIFE(slot, value) do { } while (0)
 #endif
 
-#ifndef FA_BWD_SPLIT_DRAIN
-#define FA_BWD_SPLIT_DRAIN 0  // d=128: the compute warpgroups reduce dQ columns 64-127 from registers (red.global.v4)
-                              // 1: for every query tile   2: only for a CTA's last tile   0: never.  Measured at C2:
-                              // 1 -> 689, 2 -> 903, 0 -> 915 TFLOP/s (the LSU reduce path is the slower one), so off
-#endif
-
 namespace fa {
 
 struct BwdParams {
@@ -72,6 +66,8 @@ struct BwdParams {
   float* dq_accum;        // fp32 dQ accumulator (bh, n_q, D) with slice stride dq_bh_stride (elements)
   long long dq_bh_stride;
   int n_q, n_kv, bh, causal, diag, nqt, nkt, group_log2;
+  int d;  // true head dim (<= D); the tensor maps zero-fill / clip the columns in [d, D)
+  int accum_kv;  // 0: dk / dv written in the input dtype   1: fp32 partials reduce-added into travelling accumulators
   float scale_log2, scale;
 };
 
@@ -118,8 +114,6 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
   using Cfg = BwdCfg<D>;
   constexpr int kSub = Cfg::kSub;
   constexpr int kChunks = D / 64;
-  constexpr int kSplitMode = D == 128 ? FA_BWD_SPLIT_DRAIN : 0;
-  constexpr bool kSplitDrain = kSplitMode == 1;  // compute warpgroups take part in every tile's drain
 
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* k_smem = smem + Cfg::kOffK;
@@ -134,7 +128,7 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
   const int warp = static_cast<int>(warp_uniform(threadIdx.x >> 5));
   const int lane = threadIdx.x & 31;
 
-  // Work-item order through the grid shape (see work_item() in ptx.cuh; no division in the kernel): x = slice inside
+  // Work-item order through the grid shape (see the note on work-item order in ptx.cuh; no division in the kernel): x = slice inside
   // its group (fastest), y = kv tile j (ascending = heaviest first under the causal mask), z = slice group; tile
   // indices beyond the y limit of a grid are folded into x above the slice bits.
   const int j = static_cast<int>(((blockIdx.x >> p.group_log2) << kRankBitsY) + blockIdx.y);
@@ -155,18 +149,7 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
     i_min = first > 0 ? first / kT : 0;
   }
   const int n_iter = p.nqt > i_min ? p.nqt - i_min : 0;
-  // Each CTA walks its query tiles from a different starting point (rotated by its kv-tile index): the CTAs of one
-  // slice then reduce-add into DIFFERENT dQ tiles at any moment instead of all hammering the same L2 lines
-  // (the L2 atomic unit serialises per address).
-#ifndef FA_BWD_ROTATE
-#define FA_BWD_ROTATE 0  // measured: -4% (worse L2 locality for Q/dO, no gain on the reduce)
-#endif
-  const int rot = (FA_BWD_ROTATE && n_iter > 0) ? (j % n_iter) : 0;
-  auto tile_of = [&](int it) {
-    int r = it + rot;
-    if (r >= n_iter) r -= n_iter;
-    return i_min + r;
-  };
+  auto tile_of = [&](int it) { return i_min + it; };  // query tiles are walked in ascending order
 
   if (threadIdx.x == 0 && (smem_u32(smem) & 1023u)) {
     printf("fa_sm100 bwd: dynamic smem base not 1024-aligned\n");
@@ -187,19 +170,13 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
     for (int c = 0; c < kChunks; ++c)
       tma_load_3d(do_smem + st * Cfg::kTileBytes + c * kSub, &tm_do, &bars[kBarDOFull0 + st], c * 64, i * kT, bh);
   };
-#ifndef FA_BWD_DK_FROM_SMEM
-#define FA_BWD_DK_FROM_SMEM 0  // 1: dQ issued before dK, dK reads dS^T from shared memory (measured: slower)
-#endif
-#ifndef FA_BWD_SPLIT_DS
-#define FA_BWD_SPLIT_DS 1  // dK's first half is issued as soon as the first half of every dS^T row is in TMEM
-#endif
   // The producer lane initialises the barriers and starts K, V and the first two query tiles BEFORE the block-wide
   // sync, so their TMA latency overlaps the TMEM allocation and the rest of the prologue.
   if (warp == 12 && lane == 0) {
     for (int b = 0; b < kBarCount; ++b) {
       uint32_t count = 1u;
       if (b == kBarPReady || b == kBarDSReady || b == kBarDSHalf) count = 256u;
-      if (b == kBarDQDrained) count = kSplitDrain ? 384u : 128u;
+      if (b == kBarDQDrained) count = 128u;
       // operands shared by both MMA streams are released by two commits
       if (b == kBarQEmpty0 || b == kBarQEmpty1 || b == kBarDOEmpty0 || b == kBarDOEmpty1 || b == kBarDKVDone)
         count = 2u;
@@ -277,7 +254,6 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
       const uint32_t q_km = umma_desc_lo(smem_u32(q_smem), 16), do_km = umma_desc_lo(smem_u32(do_smem), 16);
       const uint32_t k_mn = umma_desc_lo(smem_u32(k_smem), kSub), q_mn = umma_desc_lo(smem_u32(q_smem), kSub);
       const uint32_t do_mn = umma_desc_lo(smem_u32(do_smem), kSub), ds_mn = umma_desc_lo(smem_u32(ds_smem), kT * 128);
-      const uint32_t ds_km = umma_desc_lo(smem_u32(ds_smem), 16);
 
       // D[kv, q] = A[kv, :] . B[q, :]   (both K-major, contraction over the head dim)
       auto mma_kmajor = [&](uint32_t d_col, uint32_t a_lo, uint32_t b_lo) {
@@ -311,18 +287,6 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
         for (int kk = 0; kk < kT / 16; ++kk)
           umma_ss(tmem_base + kColDPT, umma_desc(ds_mn + kk * 128), umma_desc(k_mn + kk * 128), idesc_dq,
                   kk > 0 ? 1u : 0u);
-      };
-
-      // dK[kv, d] (+)= dS^T[kv, q] . Q[q, d]   (A = the dS^T tile in shared memory read K-major, B = Q MN-major).
-      // dS^T is NOT kept in TMEM: it would sit in the DPT columns that dQ overwrites, forcing dK to run before dQ,
-      // and dQ -> drain -> dP^T(next) -> dS(next) -> dQ(next) is the loop that sets the iteration period.
-      auto mma_dk = [&](uint32_t b_lo, bool acc) {
-#pragma unroll
-        for (int kk = 0; kk < kT / 16; ++kk) {
-          const uint32_t off = (kk >> 2) * ((kT * 128) >> 4) + (kk & 3) * 2;
-          umma_ss(tmem_base + kColDK, umma_desc(ds_km + off), umma_desc(b_lo + kk * 128), idesc_acc,
-                  (acc || kk > 0) ? 1u : 0u);
-        }
       };
 
       mbar_wait(&bars[kBarKV], 0);
@@ -380,32 +344,20 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
           }
           __syncwarp();
           mbar_wait(&bars[kBarQFull0 + st], (it >> 1) & 1);
-#if FA_BWD_SPLIT_DS && !FA_BWD_DK_FROM_SMEM
+          // dK(it) += dS^T Q reads the packed dS^T straight from the DPT columns (A operand in TMEM): its first half
+          // starts as soon as the first 32 queries of each warpgroup are stored ...
           mbar_wait(&bars[kBarDSHalf], it & 1);
           tc_fence_after();
           if (elect_one()) mma_from_tmem_part(kColDK, kColDPT, q_mn + st * kTileLo, it > 0, 0);
           __syncwarp();
-#endif
           mbar_wait(&bars[kBarDSReady], it & 1);
           tc_fence_after();
           if (lane == 0) FA_TRACE(3, it);
           if (elect_one()) {
-#if FA_BWD_DK_FROM_SMEM
-            mma_dq();                                       // dQ(it) = dS K: heads the next tile's critical path
-            tc_commit(&bars[kBarDQFull]);
-            mma_dk(q_mn + st * kTileLo, it > 0);            // dK(it) += dS^T Q
+            mma_from_tmem_part(kColDK, kColDPT, q_mn + st * kTileLo, true, 1);  // ... the second half once all are
             tc_commit(&bars[kBarQEmpty0 + st]);
-#elif FA_BWD_SPLIT_DS
-            mma_from_tmem_part(kColDK, kColDPT, q_mn + st * kTileLo, true, 1);  // second half of dK(it) += dS^T Q
-            tc_commit(&bars[kBarQEmpty0 + st]);
-            mma_dq();                                                            // dQ(it) = dS K overwrites dS^T
+            mma_dq();  // dQ(it) = dS K overwrites the DPT columns: it must follow dK(it) in this (in-order) stream
             tc_commit(&bars[kBarDQFull]);
-#else
-            mma_from_tmem(kColDK, kColDPT, q_mn + st * kTileLo, it > 0);  // dK(it) += dS^T Q (reads dS^T before ...
-            tc_commit(&bars[kBarQEmpty0 + st]);
-            mma_dq();                                                      // ... dQ(it) = dS K overwrites it)
-            tc_commit(&bars[kBarDQFull]);
-#endif
           }
           __syncwarp();
         }
@@ -441,9 +393,7 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
               make_float4(v[off + 4 * c], v[off + 4 * c + 1], v[off + 4 * c + 2], v[off + 4 * c + 3]);
       };
       auto reduce_chunk = [&](int cb, int col) {
-#ifndef FA_BWD_EXPERIMENT_NO_DQ_REDUCE  // timing experiment only: results are wrong without it
-        tma_reduce_add_3d(&tm_dq, dq_smem + cb * Cfg::kDqStageBytes, col, i * kT, bh);
-#endif
+        if (col < p.d) tma_reduce_add_3d(&tm_dq, dq_smem + cb * Cfg::kDqStageBytes, col, i * kT, bh);
         tma_store_commit();
       };
       tmem_ld32(tmem_base + lane_sel + kColDPT, reinterpret_cast<uint32_t*>(v));
@@ -451,8 +401,7 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
       tc_wait_ld();
       stage_chunk(0, 0);
       stage_chunk(1, 32);
-      const bool split_now = kSplitMode == 1 || (kSplitMode == 2 && it == n_iter - 1);
-      if (D == 128 && !split_now) {  // second 64 columns straight away: TMEM goes back before any TMA bookkeeping
+      if (D == 128) {  // second 64 columns straight away: TMEM goes back before any TMA bookkeeping
         tmem_ld32(tmem_base + lane_sel + kColDPT + 64, reinterpret_cast<uint32_t*>(v));
         tmem_ld32(tmem_base + lane_sel + kColDPT + 96, reinterpret_cast<uint32_t*>(v) + 32);
         tc_wait_ld();
@@ -466,7 +415,7 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
         reduce_chunk(0, 0);
         reduce_chunk(1, 32);
       }
-      if (D == 128 && !split_now) {
+      if (D == 128) {
         // columns 64-127 follow through the same two buffers, each as soon as its previous reduce has been read, so
         // the reduce engine (about 40 B/ns per SM, measured) never waits for the staging stores of a whole half
         if (row == 0) {
@@ -505,50 +454,6 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
     const uint32_t t_st = tmem_base + lane_sel + kColST + col_base;
     const uint32_t t_dpt = tmem_base + lane_sel + kColDPT + col_base;
     uint8_t* ds_row = ds_smem + wg * (kT * 128) + r * 128;
-
-    // d = 128: this warpgroup's share of the dQ(it) drain -- 32 of the columns 64-127, straight from TMEM to dq_accum
-    // with red.global.v4.  The compute warps idle for about a third of every iteration and TMEM lane r is query row
-    // r for dQ, so this halves what goes through the staging buffers and the TMA reduce (shared-memory port, the
-    // busiest unit of this kernel) and halves the drain left over when the CTA has nothing else to do.
-    // Lane pairs exchange halves so that each warp-wide red covers 16 rows x one full 32-byte sector.
-    auto drain_dq_share = [&](int it_prev) {
-      mbar_wait(&bars[kBarDQFull], it_prev & 1);
-      tc_fence_after();
-      const int q_row = tile_of(it_prev) * kT + r;
-      const bool odd = (lane & 1) != 0;
-      const int row_a = odd ? q_row - 1 : q_row;  // first red of a pair goes to the even lane's row ...
-      const int row_b = row_a + 1;                // ... the second to the odd lane's
-      float* base = p.dq_accum + static_cast<long long>(bh) * p.dq_bh_stride + 64 + wg * 32 + (odd ? 4 : 0);
-      float* pa = base + static_cast<long long>(row_a) * D;
-      float* pb = base + static_cast<long long>(row_b) * D;
-      const bool ok_a = row_a < p.n_q, ok_b = row_b < p.n_q;
-      const uint32_t t_dq = tmem_base + lane_sel + kColDPT + 64 + wg * 32;
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        float v[16];
-        tmem_ld16(t_dq + h * 16, reinterpret_cast<uint32_t*>(v));
-        tc_wait_ld();
-        if (h == 1 && kSplitDrain) {
-          tc_fence_before();
-          mbar_arrive(&bars[kBarDQDrained]);
-        }
-#pragma unroll
-        for (int m = 0; m < 2; ++m) {
-          float x[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e)  // even lanes hand over their upper four values, odd lanes their lower four
-            x[e] = __shfl_xor_sync(0xffffffffu, odd ? v[8 * m + e] : v[8 * m + 4 + e], 1);
-          const int col = h * 16 + m * 8;
-          if (!odd) {
-            if (ok_a) red_add_v4(pa + col, v[8 * m], v[8 * m + 1], v[8 * m + 2], v[8 * m + 3]);
-            if (ok_b) red_add_v4(pb + col, x[0], x[1], x[2], x[3]);
-          } else {
-            if (ok_a) red_add_v4(pa + col, x[0], x[1], x[2], x[3]);
-            if (ok_b) red_add_v4(pb + col, v[8 * m + 4], v[8 * m + 5], v[8 * m + 6], v[8 * m + 7]);
-          }
-        }
-      }
-    };
 
     for (int it = 0; it < n_iter; ++it) {
       const int i = tile_of(it), st = it & 1;
@@ -602,16 +507,13 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
       tc_fence_before();
       mbar_arrive(&bars[kBarPReady]);
       if (threadIdx.x == 0) FA_TRACE(5, it);
-      if constexpr (kSplitDrain) {
-        if (it > 0) drain_dq_share(it - 1);  // must precede the dP^T(it) wait: dP^T(it) is issued once dQ(it-1) is out
-      }
-
       mbar_wait(&bars[kBarDPFull], it & 1);
       tc_fence_after();
       if (threadIdx.x == 0) FA_TRACE(6, it);
       {
         // dS^T = P o (dP^T - delta) in four 16-column steps; the TMEM load of step c+1 is in flight while step c is
-        // computed, converted and written to the shared-memory tile (the only copy: dK and dQ both read it from there)
+        // computed, converted and written twice: packed over the consumed dP^T columns in TMEM (A operand of dK) and to
+        // the swizzled shared-memory tile (A operand of dQ, which needs the un-transposed view)
         float dp[2][16];
         tmem_ld16(t_dpt, reinterpret_cast<uint32_t*>(dp[0]));
         tc_wait_ld();
@@ -638,30 +540,21 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
                 make_uint4(pk[4 * ch], pk[4 * ch + 1], pk[4 * ch + 2], pk[4 * ch + 3]);
           }
           if (c + 1 < 4) tc_wait_ld();
-#if !FA_BWD_DK_FROM_SMEM
           tmem_st8(t_dpt + c * 8, pk);  // packed dS^T over the dP^T columns this thread has already consumed
-#if FA_BWD_SPLIT_DS
           if (c == 1) {  // first 32 queries of this warpgroup are in TMEM: dK can start on them
             tc_wait_st();
             tc_fence_before();
             mbar_arrive(&bars[kBarDSHalf]);
           }
-#endif
-#endif
         }
       }
-#if !FA_BWD_DK_FROM_SMEM
       tc_wait_st();
-#endif
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(&bars[kBarDSReady]);
       if (threadIdx.x == 0) FA_TRACE(7, it);
     }
 
-    if constexpr (kSplitMode != 0) {
-      if (n_iter > 0) drain_dq_share(n_iter - 1);
-    }
     // ------------------------------- epilogue: WG0 stores dV, WG1 stores dK * scale -------------------------------
     if (threadIdx.x == 0) FA_LIFE(4, clock64());  // last dS handed over
     if (n_iter > 0) {
@@ -674,34 +567,67 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
     uint8_t* stage_tile = wg == 0 ? v_smem : k_smem;
     const uint32_t t_acc = tmem_base + lane_sel + (wg == 0 ? kColDV : kColDK);
     const float mul = wg == 0 ? 1.f : p.scale;
+    const CUtensorMap* tm = wg == 0 ? &tm_dv : &tm_dk;
+    if (!p.accum_kv) {
+      // 16-bit results: the whole tile goes through the (dead) V / K buffer and out with one TMA store per 64 columns
 #pragma unroll
-    for (int q4 = 0; q4 < D / 32; ++q4) {
-      float a[32];
-      if (n_iter > 0) {
-        tmem_ld32(t_acc + q4 * 32, reinterpret_cast<uint32_t*>(a));
-        tc_wait_ld();
-      } else {
+      for (int q4 = 0; q4 < D / 32; ++q4) {
+        float a[32];
+        if (n_iter > 0) {
+          tmem_ld32(t_acc + q4 * 32, reinterpret_cast<uint32_t*>(a));
+          tc_wait_ld();
+        } else {
 #pragma unroll
-        for (int x = 0; x < 32; ++x) a[x] = 0.f;
+          for (int x = 0; x < 32; ++x) a[x] = 0.f;
+        }
+        uint32_t pk[16];
+#pragma unroll
+        for (int x = 0; x < 16; ++x) pk[x] = pack2<kBF16>(a[2 * x] * mul, a[2 * x + 1] * mul);
+        uint8_t* sub = stage_tile + (q4 >> 1) * kSub + r * 128;
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+          const int chunk = (q4 & 1) * 4 + ch;
+          *reinterpret_cast<uint4*>(sub + ((chunk ^ (r & 7)) << 4)) =
+              make_uint4(pk[4 * ch], pk[4 * ch + 1], pk[4 * ch + 2], pk[4 * ch + 3]);
+        }
       }
-      uint32_t pk[16];
-#pragma unroll
-      for (int x = 0; x < 16; ++x) pk[x] = pack2<kBF16>(a[2 * x] * mul, a[2 * x + 1] * mul);
-      uint8_t* sub = stage_tile + (q4 >> 1) * kSub + r * 128;
-#pragma unroll
-      for (int ch = 0; ch < 4; ++ch) {
-        const int chunk = (q4 & 1) * 4 + ch;
-        *reinterpret_cast<uint4*>(sub + ((chunk ^ (r & 7)) << 4)) =
-            make_uint4(pk[4 * ch], pk[4 * ch + 1], pk[4 * ch + 2], pk[4 * ch + 3]);
+      fence_proxy_async_smem();
+      named_bar_sync(1 + wg, 128);
+      if (r == 0) {
+        for (int ch = 0; ch < kChunks; ++ch) tma_store_3d(tm, stage_tile + ch * kSub, ch * 64, j * kT, bh);
+        tma_store_commit();
+        tma_store_wait_exit();  // K/V staging has been read; the stores complete by grid end
       }
-    }
-    fence_proxy_async_smem();
-    named_bar_sync(1 + wg, 128);
-    if (r == 0) {
-      const CUtensorMap* tm = wg == 0 ? &tm_dv : &tm_dk;
-      for (int ch = 0; ch < kChunks; ++ch) tma_store_3d(tm, stage_tile + ch * kSub, ch * 64, j * kT, bh);
-      tma_store_commit();
-      tma_store_wait_exit();  // K/V staging has been read; the stores complete by grid end
+    } else if (n_iter > 0) {
+      // fp32 accumulators that travel with the K/V block (ring attention): the partial is reduce-added in fp32, 32
+      // columns (one 128-byte swizzled row per kv row, 16 KiB) at a time, D/64 such chunks per round through the
+      // same V / K buffer.  tm_dv / tm_dk describe the fp32 accumulators here.
+      constexpr int kPerRound = D / 64;
+#pragma unroll
+      for (int round = 0; round < 2; ++round) {
+#pragma unroll
+        for (int u = 0; u < kPerRound; ++u) {
+          float a[32];
+          tmem_ld32(t_acc + (round * kPerRound + u) * 32, reinterpret_cast<uint32_t*>(a));
+          tc_wait_ld();
+          uint8_t* rowp = stage_tile + u * Cfg::kDqStageBytes + r * 128;
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+            *reinterpret_cast<float4*>(rowp + ((c ^ (r & 7)) << 4)) =
+                make_float4(a[4 * c] * mul, a[4 * c + 1] * mul, a[4 * c + 2] * mul, a[4 * c + 3] * mul);
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(1 + wg, 128);
+        if (r == 0) {
+          for (int u = 0; u < kPerRound; ++u) {
+            const int col = (round * kPerRound + u) * 32;
+            if (col < p.d) tma_reduce_add_3d(tm, stage_tile + u * Cfg::kDqStageBytes, col, j * kT, bh);
+          }
+          tma_store_commit();
+          tma_store_wait_read<0>();
+        }
+        named_bar_sync(1 + wg, 128);  // the buffer is free for the next round / safe to leave
+      }
     }
   }
 
@@ -720,12 +646,12 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
 // pre-pass: delta = rowsum(dO o O), packed with lse*log2e per 128-row tile (HBM-bound: 2*D*2 + 4 B read, 8 B written
 // per query row).  One warp handles 32/(D/8) rows at a time with 16-byte loads.
 // ------------------------------------------------------------------------------------------------
-template <int D, bool kBF16>
+template <int DP, bool kBF16>
 __global__ void __launch_bounds__(256)
 fa_bwd_prepare_kernel(const uint16_t* __restrict__ o, const uint16_t* __restrict__ d_o, const float* __restrict__ lse,
                       float* __restrict__ rowstats, long long n_q, long long bh, long long nqt, long long q_bh_stride,
-                      long long lse_bh_stride) {
-  constexpr int kLanesPerRow = D / 8;
+                      long long lse_bh_stride, int d, float* __restrict__ dq_zero) {
+  constexpr int kLanesPerRow = DP / 8;  // DP = d rounded up to 64 / 128; lanes past d / 8 idle
   constexpr int kRowsPerWarp = 32 / kLanesPerRow;
   const int lane = threadIdx.x & 31;
   const int sub = lane / kLanesPerRow, li = lane % kLanesPerRow;
@@ -738,8 +664,8 @@ fa_bwd_prepare_kernel(const uint16_t* __restrict__ o, const uint16_t* __restrict
     const long long b = r / rows_pad, rr = r % rows_pad;
     const bool valid = rr < n_q;
     float acc = 0.f;
-    if (valid) {
-      const long long off = b * q_bh_stride + rr * D + li * 8;
+    if (valid && li * 8 < d) {
+      const long long off = b * q_bh_stride + rr * d + li * 8;
       const uint4 a = *reinterpret_cast<const uint4*>(o + off);
       const uint4 g = *reinterpret_cast<const uint4*>(d_o + off);
       const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, gw[4] = {g.x, g.y, g.z, g.w};
@@ -763,22 +689,39 @@ fa_bwd_prepare_kernel(const uint16_t* __restrict__ o, const uint16_t* __restrict
       tile[128 + rr % kT] = valid ? -acc : 0.f;
     }
   }
+  // optional: zero-fill the fp32 dQ accumulator the main pass reduce-adds into (saves the caller a separate memset
+  // launch; the stores overlap the O / dO reads above)
+  if (dq_zero != nullptr) {
+    const long long per_slice = n_q * d / 4;  // float4 per slice (d % 8 == 0)
+    const long long total_vec = bh * per_slice;
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total_vec; i += stride) {
+      const long long b = i / per_slice, e = i % per_slice;
+      reinterpret_cast<float4*>(dq_zero + b * q_bh_stride)[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
 }
 
 template <int D, bool kBF16>
 static int launch_bwd(const Geometry& g, const void* q, const void* k, const void* v, const void* d_o,
-                      const float* rowstats, float* dq_accum, void* dk, void* dv, cudaStream_t stream) {
+                      const float* rowstats, float* dq_accum, void* dk, void* dv, bool accum_kv,
+                      long long acc_bh_stride, cudaStream_t stream) {
   using Cfg = BwdCfg<D>;
   const int elem = kBF16 ? kElemBF16 : kElemF16;
   CUtensorMap tm_q, tm_k, tm_v, tm_do, tm_dq, tm_dk, tm_dv;
   int rc;
-  if ((rc = make_tmap_3d(&tm_q, q, elem, D, g.n_q, g.bh, g.q_bh_stride, 64, kT))) return rc;
-  if ((rc = make_tmap_3d(&tm_do, d_o, elem, D, g.n_q, g.bh, g.q_bh_stride, 64, kT))) return rc;
-  if ((rc = make_tmap_3d(&tm_k, k, elem, D, g.n_kv, g.bh, g.kv_bh_stride, 64, kT))) return rc;
-  if ((rc = make_tmap_3d(&tm_v, v, elem, D, g.n_kv, g.bh, g.kv_bh_stride, 64, kT))) return rc;
-  if ((rc = make_tmap_3d(&tm_dk, dk, elem, D, g.n_kv, g.bh, g.kv_bh_stride, 64, kT))) return rc;
-  if ((rc = make_tmap_3d(&tm_dv, dv, elem, D, g.n_kv, g.bh, g.kv_bh_stride, 64, kT))) return rc;
-  if ((rc = make_tmap_3d(&tm_dq, dq_accum, kElemF32, D, g.n_q, g.bh, g.q_bh_stride, 32, kT))) return rc;
+  if ((rc = make_tmap_3d(&tm_q, q, elem, g.d, g.n_q, g.bh, g.q_bh_stride, 64, kT))) return rc;
+  if ((rc = make_tmap_3d(&tm_do, d_o, elem, g.d, g.n_q, g.bh, g.q_bh_stride, 64, kT))) return rc;
+  if ((rc = make_tmap_3d(&tm_k, k, elem, g.d, g.n_kv, g.bh, g.kv_bh_stride, 64, kT))) return rc;
+  if ((rc = make_tmap_3d(&tm_v, v, elem, g.d, g.n_kv, g.bh, g.kv_bh_stride, 64, kT))) return rc;
+  if (accum_kv) {  // fp32 accumulators, 32-column boxes like dq_accum
+    if ((rc = make_tmap_3d(&tm_dk, dk, kElemF32, g.d, g.n_kv, g.bh, acc_bh_stride, 32, kT))) return rc;
+    if ((rc = make_tmap_3d(&tm_dv, dv, kElemF32, g.d, g.n_kv, g.bh, acc_bh_stride, 32, kT))) return rc;
+  } else {
+    if ((rc = make_tmap_3d(&tm_dk, dk, elem, g.d, g.n_kv, g.bh, g.kv_bh_stride, 64, kT))) return rc;
+    if ((rc = make_tmap_3d(&tm_dv, dv, elem, g.d, g.n_kv, g.bh, g.kv_bh_stride, 64, kT))) return rc;
+  }
+  if ((rc = make_tmap_3d(&tm_dq, dq_accum, kElemF32, g.d, g.n_q, g.bh, g.q_bh_stride, 32, kT))) return rc;
 
   BwdParams p;
   p.rowstats = rowstats;
@@ -789,6 +732,8 @@ static int launch_bwd(const Geometry& g, const void* q, const void* k, const voi
   p.bh = static_cast<int>(g.bh);
   p.causal = g.causal;
   p.diag = g.diag;
+  p.d = g.d;
+  p.accum_kv = accum_kv ? 1 : 0;
   p.nqt = static_cast<int>((g.n_q + kT - 1) / kT);
   p.nkt = static_cast<int>((g.n_kv + kT - 1) / kT);
   p.group_log2 = sched_group_log2(g.causal != 0, p.nkt, g.bh);
@@ -823,16 +768,17 @@ extern "C" size_t fa_sm100_rowstats_bytes(const fa_sm100_shape* s) {
 }
 
 extern "C" int fa_sm100_bwd_prepare(const fa_sm100_shape* s, const void* o, const void* d_o, const float* lse,
-                                    float* rowstats, void* stream) {
+                                    float* rowstats, float* dq_accum_zero, void* stream) {
   fa::Geometry g;
   int rc = fa::check_shape(s, &g);
   if (rc) return rc;
   if (!fa::aligned16(o) || !fa::aligned16(d_o) || lse == nullptr || !fa::aligned16(rowstats))
     return FA_SM100_EINVAL_PTR;
+  if (dq_accum_zero != nullptr && !fa::aligned16(dq_accum_zero)) return FA_SM100_EINVAL_PTR;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const long long nqt = (g.n_q + fa::kT - 1) / fa::kT;
   const long long rows = g.bh * nqt * fa::kT;
-  const int rows_per_block = (256 / 32) * (32 / (g.d / 8));
+  const int rows_per_block = (256 / 32) * (32 / (g.dp / 8));
   long long grid = (rows + rows_per_block - 1) / rows_per_block;
   if (grid > 148 * 16) grid = 148 * 16;
   const uint16_t* op = static_cast<const uint16_t*>(o);
@@ -840,8 +786,8 @@ extern "C" int fa_sm100_bwd_prepare(const fa_sm100_shape* s, const void* o, cons
   const bool bf = g.dtype == FA_SM100_DTYPE_BF16;
 #define FA_LAUNCH_PREP(DD, BF)                                                                                  \
   fa::fa_bwd_prepare_kernel<DD, BF><<<static_cast<unsigned>(grid), 256, 0, st>>>(op, gp, lse, rowstats, g.n_q, g.bh, \
-                                                                                  nqt, g.q_bh_stride, g.lse_bh_stride)
-  if (g.d == 128) {
+                                                                                  nqt, g.q_bh_stride, g.lse_bh_stride, g.d, dq_accum_zero)
+  if (g.dp == 128) {
     if (bf) FA_LAUNCH_PREP(128, true); else FA_LAUNCH_PREP(128, false);
   } else {
     if (bf) FA_LAUNCH_PREP(64, true); else FA_LAUNCH_PREP(64, false);
@@ -850,22 +796,41 @@ extern "C" int fa_sm100_bwd_prepare(const fa_sm100_shape* s, const void* o, cons
   return fa::launch_status();
 }
 
+namespace fa {
+static int bwd_dispatch(const fa_sm100_shape* s, const void* q, const void* k, const void* v, const void* d_o,
+                        const float* rowstats, float* dq_accum, void* dk, void* dv, bool accum_kv,
+                        long long acc_bh_stride, void* stream) {
+  Geometry g;
+  int rc = check_shape(s, &g);
+  if (rc) return rc;
+  if (!aligned16(q) || !aligned16(k) || !aligned16(v) || !aligned16(d_o) || !aligned16(rowstats) ||
+      !aligned16(dq_accum) || !aligned16(dk) || !aligned16(dv))
+    return FA_SM100_EINVAL_PTR;
+  if (accum_kv) {
+    if (acc_bh_stride == 0) acc_bh_stride = g.n_kv * g.d;
+    if (acc_bh_stride < g.n_kv * g.d || (acc_bh_stride % 4)) return FA_SM100_EINVAL_SHAPE;
+  }
+  if ((rc = check_device())) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const bool bf = g.dtype == FA_SM100_DTYPE_BF16;
+  if (g.dp == 128) {
+    return bf ? launch_bwd<128, true>(g, q, k, v, d_o, rowstats, dq_accum, dk, dv, accum_kv, acc_bh_stride, st)
+              : launch_bwd<128, false>(g, q, k, v, d_o, rowstats, dq_accum, dk, dv, accum_kv, acc_bh_stride, st);
+  }
+  return bf ? launch_bwd<64, true>(g, q, k, v, d_o, rowstats, dq_accum, dk, dv, accum_kv, acc_bh_stride, st)
+            : launch_bwd<64, false>(g, q, k, v, d_o, rowstats, dq_accum, dk, dv, accum_kv, acc_bh_stride, st);
+}
+}  // namespace fa
+
 extern "C" int fa_sm100_bwd(const fa_sm100_shape* s, const void* q, const void* k, const void* v, const void* d_o,
                             const float* rowstats, float* dq_accum, void* dk, void* dv, void* stream) {
-  fa::Geometry g;
-  int rc = fa::check_shape(s, &g);
-  if (rc) return rc;
-  if (!fa::aligned16(q) || !fa::aligned16(k) || !fa::aligned16(v) || !fa::aligned16(d_o) ||
-      !fa::aligned16(rowstats) || !fa::aligned16(dq_accum) || !fa::aligned16(dk) || !fa::aligned16(dv))
-    return FA_SM100_EINVAL_PTR;
-  if ((rc = fa::check_device())) return rc;
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (g.d == 128) {
-    return g.dtype == FA_SM100_DTYPE_BF16 ? fa::launch_bwd<128, true>(g, q, k, v, d_o, rowstats, dq_accum, dk, dv, st)
-                                          : fa::launch_bwd<128, false>(g, q, k, v, d_o, rowstats, dq_accum, dk, dv, st);
-  }
-  return g.dtype == FA_SM100_DTYPE_BF16 ? fa::launch_bwd<64, true>(g, q, k, v, d_o, rowstats, dq_accum, dk, dv, st)
-                                        : fa::launch_bwd<64, false>(g, q, k, v, d_o, rowstats, dq_accum, dk, dv, st);
+  return fa::bwd_dispatch(s, q, k, v, d_o, rowstats, dq_accum, dk, dv, false, 0, stream);
+}
+
+extern "C" int fa_sm100_bwd_accum(const fa_sm100_shape* s, const void* q, const void* k, const void* v,
+                                  const void* d_o, const float* rowstats, float* dq_accum, float* dk_accum,
+                                  float* dv_accum, int64_t acc_bh_stride, void* stream) {
+  return fa::bwd_dispatch(s, q, k, v, d_o, rowstats, dq_accum, dk_accum, dv_accum, true, acc_bh_stride, stream);
 }
 
 #ifdef FA_BWD_TRACE

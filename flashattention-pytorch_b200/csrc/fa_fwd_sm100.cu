@@ -29,6 +29,7 @@ struct FwdParams {
   long long lse_bh_stride;
   long long o_bh_stride;  // elements; o_prev shares o's geometry
   int n_q, n_kv, bh, causal, diag, npairs, group_log2;
+  int d;             // true head dim (<= D): row stride of o_prev; columns [d, D) are zero-filled / clipped by TMA
   float scale_log2;  // softmax_scale * log2(e)
 };
 
@@ -124,7 +125,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
 #endif
 
   // heavy (late, for causal) tile pairs first, over groups of slices small enough for their K/V to stay L2-resident
-  // Work-item order (see work_item() in ptx.cuh for the idea), expressed through the grid shape so that the kernel
+  // Work-item order (see the note in ptx.cuh for the idea), expressed through the grid shape so that the kernel
   // needs no division: x = slice inside its group (fastest), y = tile-pair rank (heaviest first), z = slice group.
   // Ranks beyond the y limit of a grid are folded into x above the slice bits.
   const uint32_t rank = ((blockIdx.x >> p.group_log2) << kRankBitsY) + blockIdx.y;
@@ -413,7 +414,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
     const uint32_t* o_prev_row =
         merge ? reinterpret_cast<const uint32_t*>(static_cast<const uint16_t*>(p.o_prev) +
                                                   static_cast<long long>(bh) * p.o_bh_stride +
-                                                  static_cast<long long>(row_l) * D)
+                                                  static_cast<long long>(row_l) * p.d)
               : nullptr;
 #pragma unroll
     for (int q4 = 0; q4 < D / 32; ++q4) {
@@ -429,7 +430,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
 #pragma unroll
       for (int x = 0; x < 16; ++x) {
         float a = o[2 * x] * w_cur, b = o[2 * x + 1] * w_cur;
-        if (merge) {
+        if (merge && q4 * 32 + 2 * x < p.d) {
           const float2 pv = unpack2<kBF16>(o_prev_row[q4 * 16 + x]);
           a = fmaf(pv.x, w_prev, a);
           b = fmaf(pv.y, w_prev, b);
@@ -474,10 +475,10 @@ static int launch_fwd(const Geometry& g, const void* q, const void* k, const voi
   const int elem = kBF16 ? kElemBF16 : kElemF16;
   CUtensorMap tm_q, tm_k, tm_v, tm_o;
   int rc;
-  if ((rc = make_tmap_3d(&tm_q, q, elem, D, g.n_q, g.bh, g.q_bh_stride, 64, kBM))) return rc;
-  if ((rc = make_tmap_3d(&tm_k, k, elem, D, g.n_kv, g.bh, g.kv_bh_stride, 64, kBN))) return rc;
-  if ((rc = make_tmap_3d(&tm_v, v, elem, D, g.n_kv, g.bh, g.kv_bh_stride, 64, kBN))) return rc;
-  if ((rc = make_tmap_3d(&tm_o, o, elem, D, g.n_q, g.bh, g.q_bh_stride, 64, kBM))) return rc;
+  if ((rc = make_tmap_3d(&tm_q, q, elem, g.d, g.n_q, g.bh, g.q_bh_stride, 64, kBM))) return rc;
+  if ((rc = make_tmap_3d(&tm_k, k, elem, g.d, g.n_kv, g.bh, g.kv_bh_stride, 64, kBN))) return rc;
+  if ((rc = make_tmap_3d(&tm_v, v, elem, g.d, g.n_kv, g.bh, g.kv_bh_stride, 64, kBN))) return rc;
+  if ((rc = make_tmap_3d(&tm_o, o, elem, g.d, g.n_q, g.bh, g.q_bh_stride, 64, kBM))) return rc;
 
   FwdParams p;
   p.lse = lse;
@@ -490,6 +491,7 @@ static int launch_fwd(const Geometry& g, const void* q, const void* k, const voi
   p.bh = static_cast<int>(g.bh);
   p.causal = g.causal;
   p.diag = g.diag;
+  p.d = g.d;
   p.npairs = static_cast<int>((g.n_q + 2 * kBM - 1) / (2 * kBM));
   p.group_log2 = sched_group_log2(g.causal != 0, p.npairs, g.bh);
   while (((g.bh + (1ll << p.group_log2) - 1) >> p.group_log2) > 65535) ++p.group_log2;  // grid.z limit
@@ -525,7 +527,7 @@ extern "C" int fa_sm100_fwd(const fa_sm100_shape* s, const void* q, const void* 
   if ((o_prev == nullptr) != (lse_prev == nullptr)) return FA_SM100_EINVAL_PTR;
   if ((rc = fa::check_device())) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (g.d == 128) {
+  if (g.dp == 128) {
     return g.dtype == FA_SM100_DTYPE_BF16 ? fa::launch_fwd<128, true>(g, q, k, v, o, lse, o_prev, lse_prev, st)
                                           : fa::launch_fwd<128, false>(g, q, k, v, o, lse, o_prev, lse_prev, st);
   }

@@ -53,14 +53,17 @@ inline bool aligned16(const void* p) { return p != nullptr && (reinterpret_cast<
 
 struct Geometry {
   long long bh, n_q, n_kv, q_bh_stride, kv_bh_stride, lse_bh_stride;
-  int d, dtype, causal, diag;  // diag = q_row0 - kv_col0: key c visible to query r iff c <= r + diag
+  int d, dp, dtype, causal, diag;  // diag = q_row0 - kv_col0: key c visible to query r iff c <= r + diag
+                                   // dp = d rounded up to the kernel variant's head dim (64 / 128)
   float scale;
 };
 
 inline int check_shape(const fa_sm100_shape* s, Geometry* g) {
   if (!s) return FA_SM100_EINVAL_PTR;
   if (s->dtype != FA_SM100_DTYPE_F16 && s->dtype != FA_SM100_DTYPE_BF16) return FA_SM100_EINVAL_DTYPE;
-  if (s->d != 64 && s->d != 128) return FA_SM100_EINVAL_HEADDIM;
+  // any multiple of 8 up to 128: rows stay 16-byte aligned for TMA, and the tensor maps carry the true d, so the
+  // columns between d and the kernel variant's 64 / 128 are zero-filled on load and clipped on store (no pad copies)
+  if (s->d < 8 || s->d > 128 || (s->d % 8)) return FA_SM100_EINVAL_HEADDIM;
   if (s->bh <= 0 || s->n_q <= 0 || s->n_kv <= 0) return FA_SM100_EINVAL_SHAPE;
   if (s->n_q > (1ll << 30) || s->n_kv > (1ll << 30) || s->bh > (1ll << 30)) return FA_SM100_EINVAL_SHAPE;
   if (!(s->softmax_scale > 0.f) || !std::isfinite(s->softmax_scale)) return FA_SM100_EINVAL_SCALE;
@@ -70,6 +73,7 @@ inline int check_shape(const fa_sm100_shape* s, Geometry* g) {
   g->n_q = s->n_q;
   g->n_kv = s->n_kv;
   g->d = s->d;
+  g->dp = s->d <= 64 ? 64 : 128;
   g->dtype = s->dtype;
   g->causal = s->causal ? 1 : 0;
   g->diag = static_cast<int>(diag);
@@ -93,8 +97,8 @@ inline int check_device() {
   return major == 10 ? FA_SM100_OK : FA_SM100_EDEVICE;
 }
 
-// log2 of the slices per scheduling group for cost-skewed (causal) grids: about two waves of CTAs per group (see
-// work_item()).  FA_SM100_SCHED_GROUP overrides the group size (tuning knob: 1 = slice-major order).
+// log2 of the slices per scheduling group for cost-skewed (causal) grids: about two waves of CTAs per group (see the
+// note on work-item order in ptx.cuh).  FA_SM100_SCHED_GROUP overrides the group size (tuning knob: 1 = slice-major order).
 inline int sched_group_log2(bool skewed, long long n_ranks, long long n_slices) {
   static int forced = [] {
     const char* e = std::getenv("FA_SM100_SCHED_GROUP");

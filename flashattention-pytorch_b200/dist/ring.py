@@ -9,13 +9,20 @@ Layout (causal): the sequence is cut into 2P chunks of c rows; rank r owns chunk
 as one local tensor (bh, 2c, d) = [chunk r | chunk 2P-1-r].  Every ring step is then exactly one kernel launch of equal
 cost on every rank:
 
-    source rank p == r :  chunk_a x K_a causal,  then chunk_b x [K_a | K_b] causal with q_row0 = c
+    source rank p == r :  [chunk_a | chunk_b] x [K_a | K_b]  causal in LOCAL indices (one launch)
     p <  r             :  [chunk_a | chunk_b] x K_a          (all visible, non-causal call)
     p >  r             :  chunk_b x [K_a | K_b]              (all visible, non-causal call)
 
-(the local [K_a | K_b] tensor behaves like a contiguous sequence for chunk_b because every key of K_a precedes it and
-K_b is its own diagonal block).  Partials are merged inside the forward kernel's epilogue (``merge=True``).
-Non-causal attention needs no zig-zag: every step is [all local q] x [visiting block].
+(the local [chunk_a | chunk_b] tensor behaves like a contiguous sequence under a causal mask: every key of chunk a
+precedes chunk b, the rows between them belong to other ranks, and K_b is chunk b's own diagonal block).  Partials are
+merged inside the forward kernel's epilogue (``merge=True``).  Non-causal attention needs no zig-zag: every step is
+[all local q] x [visiting block].
+
+Backward: dQ accumulates locally in fp32.  The dK/dV of a K/V block accumulate in fp32 buffers that TRAVEL with the
+block, and the kernel reduce-adds its partials straight into them (``dk_accum``/``dv_accum``: no 16-bit rounding of
+partials, no separate add pass).  Each block is handled as two key halves (chunk a / chunk b) with their own
+accumulators and launches, so an accumulator posted by the previous rank after ITS first-half launch has half a step
+to cross NVLink before this rank needs it: the transfer stays off the critical path.
 
 The schedule is written once as a generator that yields its communication requests, so the same code runs
   * under ``torch.distributed`` (``SymmMemRingDriver``: copy-engine peer copies out of symmetric memory over NVLink, the
@@ -74,7 +81,8 @@ class BlockOps:
 
     fwd: Callable      # (q, k, v, causal, scale, *, q_row0, kv_col0, out, lse, merge) -> (out, lse)
     prepare: Callable  # (o, do, lse) -> rowstats
-    bwd: Callable      # (q, k, v, o, do, lse, causal, scale, *, q_row0, kv_col0, rowstats, dq_accum) -> (None, dk, dv)
+    bwd: Callable      # (q, k, v, o, do, lse, causal, scale, *, q_row0, kv_col0, rowstats, dq_accum, dk_accum, dv_accum)
+    #                    adds the fp32 partials into dq_accum / dk_accum / dv_accum
     finish: Callable   # (dq_accum, dtype, scale) -> dq
 
 
@@ -94,8 +102,18 @@ def cuda_block_ops() -> BlockOps:
 Coroutine = Generator[tuple, object, tuple]
 
 
+def _check_local(q, k, v, causal):
+    if q.dim() != 3 or k.shape != v.shape or k.shape[0] != q.shape[0] or k.shape[2] != q.shape[2]:
+        raise ValueError("ring attention: q, k, v must be (bh, n_local, d) with matching bh and d")
+    if k.shape[1] != q.shape[1]:
+        raise ValueError("ring attention: k/v must have q's n_local (every rank owns the same rows of q, k and v)")
+    if q.shape[1] % 2:
+        raise ValueError("ring attention: n_local must be even (zig-zag chunks / key halves)")
+
+
 def ring_forward(ops: BlockOps, rank: int, world: int, q, k, v, causal: bool, scale: float) -> Coroutine:
     """q, k, v: local (bh, n_local, d).  Returns (o, lse) for the local rows."""
+    _check_local(q, k, v, causal)
     bh, n_local, d = q.shape
     c = n_local // 2
     o = torch.empty_like(q)
@@ -109,9 +127,8 @@ def ring_forward(ops: BlockOps, rank: int, world: int, q, k, v, causal: bool, sc
         kb, vb = kv
         if not causal:
             ops.fwd(q, kb, vb, False, scale, out=o, lse=lse, merge=step > 0)
-        elif src == rank:
-            ops.fwd(q[:, :c], kb[:, :c], vb[:, :c], True, scale, out=o[:, :c], lse=lse[:, :c], merge=False)
-            ops.fwd(q[:, c:], kb, vb, True, scale, q_row0=c, kv_col0=0, out=o[:, c:], lse=lse[:, c:], merge=False)
+        elif src == rank:  # own block: the local rows are causally ordered as they lie
+            ops.fwd(q, kb, vb, True, scale, out=o, lse=lse, merge=False)
         elif src < rank:
             ops.fwd(q, kb[:, :c], vb[:, :c], False, scale, out=o, lse=lse, merge=True)
         else:
@@ -122,57 +139,54 @@ def ring_forward(ops: BlockOps, rank: int, world: int, q, k, v, causal: bool, sc
 
 
 def ring_backward(ops: BlockOps, rank: int, world: int, q, k, v, o, lse, do, causal: bool, scale: float) -> Coroutine:
-    """Returns (dq, dk, dv) for the local rows.  dQ accumulates locally in fp32; each K/V block travels with its fp32
-    dK/dV accumulators and is home again, complete, after ``world`` hops."""
+    """Returns (dq, dk, dv) for the local rows.  dQ accumulates locally in fp32; each K/V block travels with fp32 dK/dV
+    accumulators (one pair per key half) that every rank's kernel adds into, and is home, complete, after ``world``
+    hops."""
+    _check_local(q, k, v, causal)
     bh, n_local, d = q.shape
     c = n_local // 2
-    dq_acc = torch.zeros(q.shape, device=q.device, dtype=torch.float32)
-    stats_all = ops.prepare(o, do, lse)
-    stats_a = stats_b = None
-    if causal:
-        stats_a = ops.prepare(o[:, :c], do[:, :c], lse[:, :c])
-        stats_b = ops.prepare(o[:, c:], do[:, c:], lse[:, c:])
+    dq_acc = torch.empty(q.shape, device=q.device, dtype=torch.float32)
+    stats_all = ops.prepare(o, do, lse, zero=dq_acc)
+    stats_b = ops.prepare(o[:, c:], do[:, c:], lse[:, c:]) if causal else None
+    halves = (slice(0, c), slice(c, n_local))
     kv = [k, v]
-    acc = [torch.zeros(k.shape, device=k.device, dtype=torch.float32),
-           torch.zeros(v.shape, device=v.device, dtype=torch.float32)]
-    acc_handle = None
+    # acc[g] = [dK, dV] of key half g of the block being visited; ours start at zero and come home after `world` hops
+    acc = [[torch.zeros((bh, c, d), device=k.device, dtype=torch.float32) for _ in range(2)] for _ in range(2)]
+    acc_handle = [None, None]
     for step in range(world):
         kv_handle = None
         if step + 1 < world:
             kv_handle = yield ("post", kv)
         src = (rank - step) % world
         kb, vb = kv
-        # partial dK/dV of the visiting block: list of (row slice, dk, dv)
-        parts = []
-        if not causal:
-            _, dk, dv = ops.bwd(q, kb, vb, None, do, None, False, scale, rowstats=stats_all, dq_accum=dq_acc)
-            parts.append((slice(None), dk, dv))
-        elif src == rank:
-            _, dk, dv = ops.bwd(q[:, :c], kb[:, :c], vb[:, :c], None, do[:, :c], None, True, scale,
-                                rowstats=stats_a, dq_accum=dq_acc[:, :c])
-            parts.append((slice(0, c), dk, dv))
-            _, dk, dv = ops.bwd(q[:, c:], kb, vb, None, do[:, c:], None, True, scale, q_row0=c, kv_col0=0,
-                                rowstats=stats_b, dq_accum=dq_acc[:, c:])
-            parts.append((slice(None), dk, dv))
-        elif src < rank:
-            _, dk, dv = ops.bwd(q, kb[:, :c], vb[:, :c], None, do, None, False, scale, rowstats=stats_all,
-                                dq_accum=dq_acc)
-            parts.append((slice(0, c), dk, dv))
-        else:
-            _, dk, dv = ops.bwd(q[:, c:], kb, vb, None, do[:, c:], None, False, scale, rowstats=stats_b,
-                                dq_accum=dq_acc[:, c:])
-            parts.append((slice(None), dk, dv))
-        if acc_handle is not None:  # accumulators of the block we are working on arrive from the previous rank
-            acc = yield ("wait", acc_handle)
-        for rows, dk, dv in parts:
-            acc[0][:, rows] += dk
-            acc[1][:, rows] += dv
-        acc_handle = yield ("post", acc)  # they move on with their block (the last hop brings ours home)
+        for g, rows in enumerate(halves):
+            if acc_handle[g] is not None:  # accumulators of this half arrive from the previous rank
+                acc[g] = yield ("wait", acc_handle[g])
+            kw = dict(dk_accum=acc[g][0], dv_accum=acc[g][1])
+            kg, vg = kb[:, rows], vb[:, rows]
+            if not causal:
+                ops.bwd(q, kg, vg, None, do, None, False, scale, rowstats=stats_all, dq_accum=dq_acc, **kw)
+            elif src == rank:
+                if g == 0:  # all local rows x chunk a: causal in local indices (chunk b sees every key of chunk a)
+                    ops.bwd(q, kg, vg, None, do, None, True, scale, rowstats=stats_all, dq_accum=dq_acc, **kw)
+                else:       # chunk b x chunk b: the diagonal block
+                    ops.bwd(q[:, c:], kg, vg, None, do[:, c:], None, True, scale, rowstats=stats_b,
+                            dq_accum=dq_acc[:, c:], **kw)
+            elif src < rank:
+                if g == 0:  # every local row sees all of chunk a of an earlier rank; its chunk b is invisible
+                    ops.bwd(q, kg, vg, None, do, None, False, scale, rowstats=stats_all, dq_accum=dq_acc, **kw)
+            else:           # only chunk b sees a later rank's keys, and it sees both halves
+                ops.bwd(q[:, c:], kg, vg, None, do[:, c:], None, False, scale, rowstats=stats_b,
+                        dq_accum=dq_acc[:, c:], **kw)
+            acc_handle[g] = yield ("post", acc[g])  # they move on with their block (the last hop brings ours home)
         if kv_handle is not None:
             kv = yield ("wait", kv_handle)
-    acc = yield ("wait", acc_handle)
+    for g in range(2):
+        acc[g] = yield ("wait", acc_handle[g])
     dq = ops.finish(dq_acc, q.dtype, scale)
-    return dq, acc[0].to(k.dtype), acc[1].to(v.dtype)
+    dk = torch.cat([acc[0][0], acc[1][0]], dim=1).to(k.dtype)
+    dv = torch.cat([acc[0][1], acc[1][1]], dim=1).to(v.dtype)
+    return dq, dk, dv
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -272,16 +286,43 @@ class SymmMemRingDriver:
     wait(handle):  the compute stream waits for that pull.  Two slots per message signature; slot reuse is safe because
     a rank reaches barrier n+1 only after its pull n, and post n+2 is issued after wait n+1."""
 
-    _drivers = {}
+    _drivers = {}          # keyed on the process-group OBJECT (an id() can be recycled after the group is collected)
+    MAX_CHANNELS = 8       # message signatures kept per driver; older symmetric slots are dropped (LRU)
 
     @classmethod
     def get(cls, group=None):
         import torch.distributed as dist
 
-        key = id(group or dist.group.WORLD)
+        key = group or dist.group.WORLD
         if key not in cls._drivers:
             cls._drivers[key] = cls(group)
         return cls._drivers[key]
+
+    @classmethod
+    def close_all(cls):
+        """Drop every cached driver and its symmetric slots (call before destroying the process groups)."""
+        for drv in cls._drivers.values():
+            drv.channels.clear()
+        cls._drivers.clear()
+
+    @staticmethod
+    def usable(example: torch.Tensor, group=None) -> bool:
+        """Symmetric-memory peer copies need a single-node group whose ring neighbours are P2P-mapped."""
+        import torch.distributed as dist
+
+        if not example.is_cuda or not dist.is_initialized() or dist.get_backend(group) != "nccl":
+            return False
+        try:
+            import torch.distributed._symmetric_memory  # noqa: F401
+        except ImportError:
+            return False
+        world = dist.get_world_size(group)
+        if world > torch.cuda.device_count():  # more ranks than local devices: the group spans nodes
+            return False
+        me = example.device.index if example.device.index is not None else torch.cuda.current_device()
+        prev_global = dist.get_global_rank(group, (dist.get_rank(group) - 1) % world) if group else (dist.get_rank() - 1) % world
+        peer = prev_global % torch.cuda.device_count()
+        return peer == me or torch.cuda.can_device_access_peer(me, peer)
 
     def __init__(self, group=None):
         import torch.distributed as dist
@@ -298,8 +339,12 @@ class SymmMemRingDriver:
         import torch.distributed._symmetric_memory as symm
 
         sig = tuple((tuple(t.shape), t.dtype) for t in tensors)
-        ch = self.channels.get(sig)
+        ch = self.channels.pop(sig, None)
+        if ch is not None:
+            self.channels[sig] = ch  # most recently used last
         if ch is None:
+            while len(self.channels) >= self.MAX_CHANNELS:
+                self.channels.pop(next(iter(self.channels)))  # least recently used symmetric slot pair
             offs, total = [], 0
             for t in tensors:
                 offs.append(total)
@@ -353,16 +398,26 @@ class SymmMemRingDriver:
             return stop.value
 
 
-def make_driver(example: torch.Tensor, group=None, transport: str = "auto"):
-    """'symm' = copy-engine peer copies over symmetric memory (CUDA only), 'nccl' = batched isend/irecv."""
+def _pick_transport(example: torch.Tensor, group=None, transport: str = "auto") -> str:
     import os
 
     transport = os.environ.get("FA_RING_TRANSPORT", transport)
-    if transport == "auto":
-        transport = "symm" if example.is_cuda else "nccl"
-    if transport == "symm":
+    if transport == "auto":  # symmetric memory only where it can work; everything else takes the send/recv driver
+        transport = "symm" if SymmMemRingDriver.usable(example, group) else "nccl"
+    return transport
+
+
+def make_driver(example: torch.Tensor, group=None, transport: str = "auto"):
+    """'symm' = copy-engine peer copies over symmetric memory (single node, P2P-mapped CUDA peers),
+    'nccl' = batched isend/irecv (NCCL on GPUs, gloo on CPU); 'auto' picks 'symm' only where it is usable."""
+    if _pick_transport(example, group, transport) == "symm":
         return SymmMemRingDriver.get(group)
     return TorchRingDriver(group)
+
+
+def ring_transport_name(example: torch.Tensor, group=None) -> str:
+    return {"symm": "symmetric-memory peer pulls on the copy engines (NVLink)",
+            "nccl": "NCCL P2P send/recv (NVLink)"}[_pick_transport(example, group)]
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -389,12 +444,35 @@ class _RingAttnFn(torch.autograd.Function):
         return dq, dk, dv, None, None, None, None
 
 
+_checked_shapes = set()
+
+
+def _check_equal_across_ranks(q, group=None):
+    """Every rank must own the same number of rows (the schedule slices received blocks at the LOCAL chunk size).
+    Checked once per (group, shape): one small all_gather."""
+    import torch.distributed as dist
+
+    if not dist.is_initialized():
+        return
+    key = (group, tuple(q.shape[-2:]))
+    if key in _checked_shapes:
+        return
+    world = dist.get_world_size(group)
+    mine = torch.tensor([q.shape[-2], q.shape[-1]], device=q.device, dtype=torch.int64)
+    everyone = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(everyone, mine, group=group)
+    if any(not torch.equal(t, mine) for t in everyone):
+        raise ValueError(f"ring attention: ranks disagree on (n_local, d): {[t.tolist() for t in everyone]}")
+    _checked_shapes.add(key)
+
+
 def ring_attention(q, k, v, causal=False, softmax_scale=None, group=None, ops: Optional[BlockOps] = None):
     """Sequence-parallel attention.  q, k, v: this rank's LOCAL rows, (bh, n_local, d) or (B, H, n_local, d), head dim
     64 or 128; for ``causal=True`` they must be laid out zig-zag (``zigzag_split``).  Returns (o, lse) for the local
     rows; differentiable."""
     if softmax_scale is None:
         softmax_scale = q.shape[-1] ** -0.5
+    _check_equal_across_ranks(q, group)
     lead = q.shape[:-2]
     qb, kb, vb = (t.reshape(-1, t.shape[-2], t.shape[-1]) for t in (q, k, v))
     o, lse = _RingAttnFn.apply(qb, kb, vb, causal, softmax_scale, group, ops)

@@ -17,6 +17,7 @@ Deliberate deviations from the reference (see DESIGN.md "Deviations"):
   * ``br``/``bc``/``stages`` are accepted and ignored: the kernel picks its own tcgen05 tile shapes and the result
     does not depend on them beyond rounding.
   * fp32 inputs and ``fp8=True`` are rejected loudly (the reference's fp8 emulation is broken).
+  * head dims that are a multiple of 8 (<= 128) run natively; others are zero-padded to the next multiple of 8.
 
 There is NO fallback: if the shared library is missing or the device is not sm_100 every call raises.
 """
@@ -61,13 +62,11 @@ ABI = {
     "fa_sm100_dq_accum_bytes": (ctypes.c_size_t, [_SP]),
     "fa_sm100_fwd": (ctypes.c_int, [_SP, _P, _P, _P, _P, _P, _P, _P, _P]),
     "fa_sm100_rowstats_bytes": (ctypes.c_size_t, [_SP]),
-    "fa_sm100_bwd_prepare": (ctypes.c_int, [_SP, _P, _P, _P, _P, _P]),
+    "fa_sm100_bwd_prepare": (ctypes.c_int, [_SP, _P, _P, _P, _P, _P, _P]),
     "fa_sm100_bwd": (ctypes.c_int, [_SP, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "fa_sm100_bwd_accum": (ctypes.c_int, [_SP, _P, _P, _P, _P, _P, _P, _P, _P, ctypes.c_int64, _P]),
     "fa_sm100_dq_finish": (ctypes.c_int, [_SP, _P, _P, _P]),
     "fa_sm100_cast_scaled": (ctypes.c_int, [_P, _P, ctypes.c_int64, ctypes.c_float, ctypes.c_int32, _P]),
-    "fa_sm100_probe_umma": (ctypes.c_int, [ctypes.c_int, ctypes.c_int32, _P, _P, _P, _P]),
-    "fa_sm100_probe_reduce_rate": (ctypes.c_int, [_P, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, _P]),
-    "fa_sm100_probe_mma_rate": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, _P]),
 }
 
 
@@ -116,12 +115,18 @@ def _dtype_code(t: torch.Tensor) -> int:
         ) from None
 
 
+MAX_HEAD_DIM = 128
+
+
 def _padded_head_dim(d: int) -> int:
-    if d <= 64:
-        return 64
-    if d <= 128:
-        return 128
-    raise NotImplementedError(f"flashattention_lab_cuda (sm_100a): head dim {d} > 128 is not supported yet")
+    """Head dims that are a multiple of 8 go to the kernels as they are (the TMA tensor maps carry the true d: columns
+    up to the kernel variant's 64 / 128 are zero-filled on load and clipped on store, no copies).  Other sizes — rows
+    would not be 16-byte aligned — are zero-padded to the next multiple of 8 by the shim."""
+    if d > MAX_HEAD_DIM:
+        raise NotImplementedError(f"flashattention_lab_cuda (sm_100a): head dim {d} > {MAX_HEAD_DIM} is not supported")
+    if os.environ.get("FA_SM100_PAD_HEAD_DIM") == "1":  # debugging aid: the round-1 behaviour (pad to 64 / 128)
+        return 64 if d <= 64 else 128
+    return (d + 7) // 8 * 8
 
 
 def _pad_d(x: torch.Tensor, dp: int) -> torch.Tensor:
@@ -154,7 +159,7 @@ def make_shape(bh, n_q, n_kv, d, dtype_code, causal, softmax_scale, q_row0=0, kv
 
 
 # ------------------------------------------------------------------------------------------------------------------
-# raw entry points (head dim already 64/128) — also used by the sharding and ring-attention drivers.
+# raw entry points (head dim a multiple of 8, <= 128) — also used by the sharding and ring-attention drivers.
 # Tensors may be views of a larger (bh, n, d) tensor along n: rows must be dense, the slice stride is free.
 # ------------------------------------------------------------------------------------------------------------------
 def _slice_stride(t: torch.Tensor) -> int:
@@ -164,7 +169,10 @@ def _slice_stride(t: torch.Tensor) -> int:
     elif t.dim() == 2:
         if t.stride(1) != 1:
             raise RuntimeError("lse rows must be dense")
-    return t.stride(0) if t.shape[0] > 1 else (t.shape[1] * (t.shape[2] if t.dim() == 3 else 1))
+    dense = t.shape[1] * (t.shape[2] if t.dim() == 3 else 1)
+    if t.shape[0] > 1 and t.stride(0) < dense:  # expanded / overlapping slices: 0 would mean "dense" to the C ABI
+        raise RuntimeError("slices must not overlap (stride(0) >= rows * head_dim); call .contiguous() first")
+    return t.stride(0) if t.shape[0] > 1 else dense
 
 
 def _same_stride(ref: torch.Tensor, *others: torch.Tensor) -> int:
@@ -180,7 +188,7 @@ def _empty_like_strided(t: torch.Tensor, dtype=None) -> torch.Tensor:
 
 
 def fwd_raw(q, k, v, causal, softmax_scale, *, q_row0=0, kv_col0=0, out=None, lse=None, merge=False):
-    """q: (bh, n_q, d), k/v: (bh, n_kv, d), d in {64,128}.  Returns (o, lse).
+    """q: (bh, n_q, d), k/v: (bh, n_kv, d), d % 8 == 0, d <= 128.  Returns (o, lse).
 
     ``merge=True`` folds the new partial into the given ``out``/``lse`` by log-sum-exp (ring attention)."""
     lib = load_library()
@@ -191,6 +199,8 @@ def fwd_raw(q, k, v, causal, softmax_scale, *, q_row0=0, kv_col0=0, out=None, ls
             raise ValueError("merge=True needs out/lse from the previous step")
         out = _empty_like_strided(q)
         lse = torch.empty((bh, n_q), device=q.device, dtype=torch.float32)
+    elif lse is None:
+        raise ValueError("out= needs lse= as well")
     shape = make_shape(bh, n_q, n_kv, d, _dtype_code(q), causal, softmax_scale, q_row0, kv_col0,
                        _same_stride(q, out), _same_stride(k, v), _slice_stride(lse))
     prev_o = out.data_ptr() if merge else None
@@ -202,36 +212,63 @@ def fwd_raw(q, k, v, causal, softmax_scale, *, q_row0=0, kv_col0=0, out=None, ls
     return out, lse
 
 
-def bwd_prepare_raw(o, do, lse):
-    """Pre-pass of the backward: packs (-lse * log2e, -delta = -rowsum(dO o O)) per 128-row query tile."""
+def bwd_prepare_raw(o, do, lse, zero=None):
+    """Pre-pass of the backward: packs (-lse * log2e, -delta = -rowsum(dO o O)) per 128-row query tile.
+    ``zero``: an fp32 dQ accumulator with o's shape and slice stride to zero-fill in the same launch."""
     lib = load_library()
     bh, n_q, d = o.shape
-    shape = make_shape(bh, n_q, n_q, d, _dtype_code(o), False, 1.0, 0, 0, _same_stride(o, do), 0, _slice_stride(lse))
+    stride = _same_stride(o, do) if zero is None else _same_stride(o, do, zero)
+    if zero is not None and (zero.dtype != torch.float32 or zero.shape != o.shape):
+        raise ValueError("zero= must be an fp32 tensor with o's shape")
+    shape = make_shape(bh, n_q, n_q, d, _dtype_code(o), False, 1.0, 0, 0, stride, 0, _slice_stride(lse))
     rowstats = torch.empty(lib.fa_sm100_rowstats_bytes(ctypes.byref(shape)) // 4, device=o.device,
                            dtype=torch.float32)
     with torch.cuda.device(o.device):
         _check(lib.fa_sm100_bwd_prepare(ctypes.byref(shape), o.data_ptr(), do.data_ptr(), lse.data_ptr(),
-                                        rowstats.data_ptr(), _stream_ptr(o)), "fa_sm100_bwd_prepare")
+                                        rowstats.data_ptr(), None if zero is None else zero.data_ptr(),
+                                        _stream_ptr(o)), "fa_sm100_bwd_prepare")
     return rowstats
 
 
-def bwd_raw(q, k, v, o, do, lse, causal, softmax_scale, *, q_row0=0, kv_col0=0, rowstats=None, dq_accum=None):
-    """Backward (d in {64,128}).
+def bwd_raw(q, k, v, o, do, lse, causal, softmax_scale, *, q_row0=0, kv_col0=0, rowstats=None, dq_accum=None,
+            dk_accum=None, dv_accum=None):
+    """Backward (d % 8 == 0, d <= 128).
 
     Plain call: returns (dq, dk, dv) in the input dtype.
     Ring call (``dq_accum`` fp32 with q's shape AND strides given, ``rowstats`` from ``bwd_prepare_raw``): dQ partials
     are added into ``dq_accum`` (finish with ``dq_finish_raw`` after the last step); returns (None, dk, dv) of THIS
-    K/V block (``o``/``lse`` may then be None)."""
+    K/V block (``o``/``lse`` may then be None).  With ``dk_accum``/``dv_accum`` (fp32, k's shape) the dK/dV partials are
+    reduce-added into them in fp32 by the kernel instead, and (None, None, None) is returned."""
     lib = load_library()
     bh, n_q, d = q.shape
     n_kv = k.shape[1]
-    if rowstats is None:
-        rowstats = bwd_prepare_raw(o, do, lse)
     ring = dq_accum is not None
     if not ring:
-        dq_accum = torch.zeros(q.shape, device=q.device, dtype=torch.float32)
         if bh > 1 and _slice_stride(q) != n_q * d:
-            q, do = q.contiguous(), do.contiguous()
+            q, do, o = q.contiguous(), do.contiguous(), o.contiguous()
+        dq_accum = torch.empty(q.shape, device=q.device, dtype=torch.float32)
+        if rowstats is None:
+            rowstats = bwd_prepare_raw(o, do, lse, zero=dq_accum)  # one launch: statistics + zero-fill
+        else:
+            dq_accum.zero_()
+    elif rowstats is None:
+        rowstats = bwd_prepare_raw(o, do, lse)
+    if (dk_accum is None) != (dv_accum is None):
+        raise ValueError("dk_accum and dv_accum go together")
+    if dk_accum is not None:
+        if not ring:
+            raise ValueError("dk_accum/dv_accum need dq_accum (ring call)")
+        for t in (dk_accum, dv_accum):
+            if t.dtype != torch.float32 or t.shape != k.shape:
+                raise ValueError("dk_accum/dv_accum must be fp32 with k's shape")
+        shape = make_shape(bh, n_q, n_kv, d, _dtype_code(q), causal, softmax_scale, q_row0, kv_col0,
+                           _same_stride(q, do, dq_accum), _same_stride(k, v), 0)
+        with torch.cuda.device(q.device):
+            _check(lib.fa_sm100_bwd_accum(ctypes.byref(shape), q.data_ptr(), k.data_ptr(), v.data_ptr(), do.data_ptr(),
+                                          rowstats.data_ptr(), dq_accum.data_ptr(), dk_accum.data_ptr(),
+                                          dv_accum.data_ptr(), _same_stride(dk_accum, dv_accum), _stream_ptr(q)),
+                   "fa_sm100_bwd_accum")
+        return None, None, None
     dk = _empty_like_strided(k)
     dv = _empty_like_strided(k)
     shape = make_shape(bh, n_q, n_kv, d, _dtype_code(q), causal, softmax_scale, q_row0, kv_col0,
@@ -263,39 +300,6 @@ def cast_scaled(acc: torch.Tensor, alpha: float, dtype: torch.dtype) -> torch.Te
         _check(lib.fa_sm100_cast_scaled(acc.data_ptr(), out.data_ptr(), acc.numel(), float(alpha), _DTYPES[dtype],
                                         _stream_ptr(acc)), "fa_sm100_cast_scaled")
     return out
-
-
-def probe_umma(mode: int, a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
-    lib = load_library()
-    rows = 256 if int(mode) >= 4 else 128  # modes 4/5 drive a CTA pair: A and out have 256 rows
-    if tuple(a.shape) != (rows, 128) or tuple(b.shape) != (128, 128) or not (a.is_contiguous() and b.is_contiguous()):
-        raise ValueError(f"probe_umma mode {mode}: need contiguous a [{rows},128] and b [128,128]")
-    out = torch.empty((rows, 128), device=a.device, dtype=torch.float32)
-    with torch.cuda.device(a.device):
-        _check(lib.fa_sm100_probe_umma(int(mode), _dtype_code(a), a.data_ptr(), b.data_ptr(), out.data_ptr(),
-                                       _stream_ptr(a)), "fa_sm100_probe_umma")
-    return out
-
-
-def probe_mma_rate(pair: bool, a_from_tmem: bool, n: int, groups: int, ctas: int, device="cuda") -> None:
-    """Launch the tensor-core issue-rate probe on the current stream (the caller times it with CUDA events)."""
-    lib = load_library()
-    dev = torch.device(device)
-    with torch.cuda.device(dev):
-        stream = torch.cuda.current_stream(dev).cuda_stream
-        _check(lib.fa_sm100_probe_mma_rate(int(bool(pair)), int(bool(a_from_tmem)), int(n), int(groups), int(ctas),
-                                           stream), "fa_sm100_probe_mma_rate")
-
-
-def probe_reduce_rate(acc: torch.Tensor, nkt: int, flags: int = 0) -> None:
-    """acc: [slices, nqt*128, 128] fp32, contiguous; every element grows by nkt (launch on the current stream).
-    flags: 1 rotated walk, 2 red.global.v4 from registers instead of TMA reduce, 4 one CTA per SM."""
-    lib = load_library()
-    if acc.dtype != torch.float32 or acc.dim() != 3 or acc.shape[2] != 128 or acc.shape[1] % 128 or not acc.is_contiguous():
-        raise ValueError("probe_reduce_rate: need contiguous fp32 acc [slices, nqt*128, 128]")
-    with torch.cuda.device(acc.device):
-        _check(lib.fa_sm100_probe_reduce_rate(acc.data_ptr(), acc.shape[0], acc.shape[1] // 128, int(nkt),
-                                              int(flags), _stream_ptr(acc)), "fa_sm100_probe_reduce_rate")
 
 
 # ------------------------------------------------------------------------------------------------------------------

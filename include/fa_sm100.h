@@ -33,7 +33,7 @@ extern "C" {
 
 #define FA_SM100_OK 0
 #define FA_SM100_EINVAL_DTYPE (-1)   /* dtype is not fp16 / bf16 */
-#define FA_SM100_EINVAL_HEADDIM (-2) /* d is not 64 or 128 (the host shim zero-pads other head dims) */
+#define FA_SM100_EINVAL_HEADDIM (-2) /* d is not a multiple of 8 in [8, 128] (the shim zero-pads d % 8 != 0) */
 #define FA_SM100_EINVAL_SHAPE (-3)   /* non-positive sizes, sizes beyond int32 tile indexing, bad strides */
 #define FA_SM100_EINVAL_PTR (-4)     /* NULL or mis-aligned tensor pointer */
 #define FA_SM100_EINVAL_SCALE (-5)   /* softmax_scale must be finite and > 0 */
@@ -46,7 +46,7 @@ typedef struct fa_sm100_shape {
   int64_t bh;            /* number of independent (batch*head) slices                                  */
   int64_t n_q;           /* query rows per slice                                                       */
   int64_t n_kv;          /* key/value rows per slice                                                   */
-  int32_t d;             /* head dim: 64 or 128                                                        */
+  int32_t d;             /* head dim: any multiple of 8 up to 128 (rows stay 16-byte aligned)          */
   int32_t dtype;         /* FA_SM100_DTYPE_*                                                           */
   int32_t causal;        /* 0/1; key c is visible to query r iff kv_col0 + c <= q_row0 + r             */
   float softmax_scale;   /* S = Q K^T * softmax_scale                                                  */
@@ -61,8 +61,8 @@ int fa_sm100_version(void);
 const char* fa_sm100_strerror(int code);
 
 /* Scratch the caller must provide to the backward:
- *   dq_accum : fp32 dQ accumulator with q's geometry (bh slices of n_q * d, slice stride q_bh_stride), ZEROED by
- *              the caller before the first fa_sm100_bwd that adds into it;
+ *   dq_accum : fp32 dQ accumulator with q's geometry (bh slices of n_q * d, slice stride q_bh_stride), ZEROED before
+ *              the first fa_sm100_bwd that adds into it (by the caller, or by fa_sm100_bwd_prepare on request);
  *   rowstats : per-query-row statistics packed per 128-row tile, bh * ceil(n_q/128) * 256 floats. */
 size_t fa_sm100_dq_accum_bytes(const fa_sm100_shape* s);
 size_t fa_sm100_rowstats_bytes(const fa_sm100_shape* s);
@@ -84,9 +84,11 @@ int fa_sm100_fwd(const fa_sm100_shape* s, const void* q, const void* k, const vo
  * lse[r] * log2(e) into `rowstats`, both NEGATED: for slice b and 128-row tile t, floats [(b*T + t)*256, +128) hold
  * -lse*log2e and the next 128 hold -delta (T = ceil(n_q/128)); rows past n_q get -inf / 0 so they contribute nothing.
  * `lse` is the (bh, n_q) tensor the forward returned (lse_bh_stride applies).
+ * If `dq_accum_zero` is non-NULL the same launch also zero-fills that fp32 dQ accumulator (q's geometry), so the
+ * caller needs no separate memset before fa_sm100_bwd.
  */
 int fa_sm100_bwd_prepare(const fa_sm100_shape* s, const void* o, const void* d_o, const float* lse, float* rowstats,
-                         void* stream);
+                         float* dq_accum_zero, void* stream);
 
 /*
  * Backward main pass, KV-outer (reference csrc/fa1/fa1_bwd.cu:70-110 with the Python skip rule of
@@ -97,39 +99,20 @@ int fa_sm100_bwd_prepare(const fa_sm100_shape* s, const void* o, const void* d_o
 int fa_sm100_bwd(const fa_sm100_shape* s, const void* q, const void* k, const void* v, const void* d_o,
                  const float* rowstats, float* dq_accum, void* dk, void* dv, void* stream);
 
+/*
+ * Ring-attention form of the main pass: instead of writing dk / dv, the fp32 partials (dK already scaled) are
+ * reduce-added into `dk_accum` / `dv_accum`, fp32 (bh, n_kv, d) with slice stride `acc_bh_stride` elements (0 =>
+ * n_kv * d) -- the accumulators that travel around the ring with their K/V block.  No 16-bit rounding of partials.
+ */
+int fa_sm100_bwd_accum(const fa_sm100_shape* s, const void* q, const void* k, const void* v, const void* d_o,
+                       const float* rowstats, float* dq_accum, float* dk_accum, float* dv_accum,
+                       int64_t acc_bh_stride, void* stream);
+
 /* dq[i] = cast(dq_accum[i] * softmax_scale).  (The reference scales per tile: csrc/fa1/fa1_bwd.cu:102-103.) */
 int fa_sm100_dq_finish(const fa_sm100_shape* s, const float* dq_accum, void* dq, void* stream);
 
 /* out[i] = cast(acc[i] * alpha) for n contiguous elements: converts fp32 ring accumulators to `dtype`. */
 int fa_sm100_cast_scaled(const float* acc, void* out, int64_t n, float alpha, int32_t dtype, void* stream);
-
-/*
- * Bring-up self-test for the hand-encoded UMMA/TMA descriptors: one 128x128x128 MMA through each operand path the
- * attention kernels use.  mode 0: D = A B^T (A,B K-major smem)   1: D = A B (B MN-major smem)
- *                         2: D = A B (A from TMEM, B MN-major)   3: D = A^T B (A,B MN-major smem)
- * a, b: 128x128 row-major `dtype`; out: 128x128 fp32.  Not part of the reference surface.
- * CTA-pair forms (cluster of 2, cta_group::2, M = 256; a and out have 256 rows, b stays 128x128):
- *                         4: D = A B^T (A,B K-major smem, B rows split across the pair)
- *                         5: D = A B (A from TMEM, B MN-major, B columns split across the pair)
- */
-int fa_sm100_probe_umma(int mode, int32_t dtype, const void* a, const void* b, float* out, void* stream);
-
-/*
- * Tensor-core issue-rate probe (measurement aid, not part of the reference surface): `ctas` CTAs (CTA pairs when
- * `pair`) each stream `groups` bf16 products of shape (128 per CTA) x n x 128 -- eight UMMAs per product -- from
- * fixed operands: A from shared memory or, with `a_from_tmem`, from TMEM with B MN-major (n <= 128 then).
- * The caller times the launch: FLOPs = ctas * groups * 2 * 128 * n * 128.
- */
-int fa_sm100_probe_mma_rate(int pair, int a_from_tmem, int n, int groups, int ctas, void* stream);
-
-/*
- * L2 reduce-add rate probe (measurement aid): the backward's dQ accumulation traffic with no compute around it.
- * slices * nkt CTAs; CTA (slice, j) reduce-adds a 128x128 fp32 tile of ones into each of the nqt row tiles of
- * acc[slice] (acc: slices x (nqt*128) x 128 fp32).  flags: 1 = start at tile j (rotated walk), 2 = red.global.v4 from
- * registers instead of TMA reduce from shared memory, 4 = one CTA per SM.  Afterwards every element of acc has grown
- * by nkt.  Bytes reduced = slices * nkt * nqt * 65536.
- */
-int fa_sm100_probe_reduce_rate(float* acc, int slices, int nqt, int nkt, int flags, void* stream);
 
 #ifdef __cplusplus
 }

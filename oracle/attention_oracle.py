@@ -210,3 +210,24 @@ def error_report(actual, expected, rtol, atol):
         "violations": int(viol.sum()),
         "numel": int(diff.numel()),
     }
+
+
+def relative_error(actual, expected, tile_rows=128):
+    """Scale-aware companion of ``error_report`` for long sequences, where an absolute 5e-2 is about the RMS of the
+    gradients themselves: ||a - e|| / ||e|| over the whole tensor and the worst such ratio over ``tile_rows``-row
+    tiles of the second-to-last dimension (a late-row or single-tile accumulation error cannot hide in the total)."""
+    a, e = actual.detach().float(), expected.detach().float().to(actual.device)
+    total = float((a - e).norm() / e.norm().clamp_min(1e-30))
+    n = a.shape[-2]
+    pad = (-n) % tile_rows
+    if pad:
+        a = torch.nn.functional.pad(a, (0, 0, 0, pad))
+        e = torch.nn.functional.pad(e, (0, 0, 0, pad))
+    at = a.reshape(*a.shape[:-2], -1, tile_rows, a.shape[-1])
+    et = e.reshape(*e.shape[:-2], -1, tile_rows, e.shape[-1])
+    num = (at - et).flatten(-2).norm(dim=-1)
+    den = et.flatten(-2).norm(dim=-1)
+    ok = den > 1e-6 * float(e.norm()) / max(1, den.numel()) ** 0.5  # skip tiles that are (numerically) all zero
+    worst = float((num[ok] / den[ok]).max()) if ok.any() else 0.0
+    return {"rel_fro": total, "worst_tile_rel_fro": worst}
+

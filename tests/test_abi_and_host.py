@@ -9,16 +9,20 @@ import torch
 
 ROOT = Path(__file__).resolve().parents[1]
 HEADER = (ROOT / "include" / "fa_sm100.h").read_text()
+PROBES_HEADER = (ROOT / "include" / "fa_sm100_probes.h").read_text()
 
 
-def _declared_symbols():
-    return sorted(set(re.findall(r"\b(fa_sm100_[a-z0-9_]+)\s*\(", HEADER)) - {"fa_sm100_shape"})
+def _declared_symbols(header=HEADER):
+    return sorted(set(re.findall(r"\b(fa_sm100_[a-z0-9_]+)\s*\(", header)) - {"fa_sm100_shape", "fa_sm100_strerror"}
+                  | ({"fa_sm100_strerror"} if header is HEADER else set()))
 
 
 def test_header_declares_the_expected_surface():
     syms = _declared_symbols()
-    for needed in ("fa_sm100_fwd", "fa_sm100_bwd", "fa_sm100_bwd_prepare", "fa_sm100_dq_finish", "fa_sm100_strerror"):
+    for needed in ("fa_sm100_fwd", "fa_sm100_bwd", "fa_sm100_bwd_accum", "fa_sm100_bwd_prepare", "fa_sm100_dq_finish",
+                   "fa_sm100_strerror"):
         assert needed in syms
+    assert not any("probe" in s for s in syms), "probe kernels belong to the debug library, not the product ABI"
 
 
 def test_library_exports_every_declared_symbol():
@@ -30,6 +34,19 @@ def test_library_exports_every_declared_symbol():
     for name in _declared_symbols():
         assert hasattr(lib, name), f"libfa_sm100.so does not export {name}"
     assert set(ext.ABI) == set(_declared_symbols()), "shim ABI table and header disagree"
+
+
+def test_debug_library_exports_every_declared_probe():
+    import probes
+
+    path = probes.library_path()
+    assert path.exists(), f"{path} missing: run `python __graft_entry__.py`"
+    lib = ctypes.CDLL(str(path))
+    declared = _declared_symbols(PROBES_HEADER)
+    assert declared and all("probe" in s for s in declared)
+    for name in declared:
+        assert hasattr(lib, name), f"libfa_sm100_probes.so does not export {name}"
+    assert set(probes.ABI) == set(declared)
 
 
 def test_library_metadata_calls_work_without_gpu():
@@ -56,7 +73,8 @@ def test_argument_validation_happens_before_any_cuda_call():
         return lib.fa_sm100_fwd(ctypes.byref(s), fake, fake, fake, fake, fake, None, None, None)
 
     assert fwd(dtype_code=7) == -1
-    assert fwd(d=96) == -2
+    assert fwd(d=96) == 0 or fwd(d=96) <= -6  # multiples of 8 up to 128 pass validation (then fail on the fake device)
+    assert fwd(d=100) == -2 and fwd(d=136) == -2 and fwd(d=4) == -2
     assert fwd(n_q=0) == -3
     assert fwd(softmax_scale=0.0) == -5
     s = ext.make_shape(**good)

@@ -29,15 +29,22 @@ def _cpu_fwd(q, k, v, causal, scale, *, q_row0=0, kv_col0=0, out=None, lse=None,
     return out, lse
 
 
-def _cpu_prepare(o, do, lse):
+def _cpu_prepare(o, do, lse, zero=None):
+    if zero is not None:
+        zero.zero_()
     return {"delta_o": o.clone(), "lse": lse.clone()}
 
 
-def _cpu_bwd(q, k, v, o, do, lse, causal, scale, *, q_row0=0, kv_col0=0, rowstats=None, dq_accum=None):
+def _cpu_bwd(q, k, v, o, do, lse, causal, scale, *, q_row0=0, kv_col0=0, rowstats=None, dq_accum=None,
+             dk_accum=None, dv_accum=None):
     dq, dk, dv = blocked_backward(q, k, v, rowstats["delta_o"], do, rowstats["lse"], causal, scale, 16, 16, q_row0,
                                   kv_col0, out_dtype=torch.float32)
     dq_accum += dq / scale  # the CUDA kernel accumulates UNSCALED dQ partials; finish() applies the scale
-    return None, dk, dv
+    if dk_accum is None:
+        return None, dk, dv
+    dk_accum += dk          # ring form: fp32 partials go straight into the travelling accumulators
+    dv_accum += dv
+    return None, None, None
 
 
 def _cpu_finish(dq_accum, dtype, scale):

@@ -10,13 +10,13 @@ sys.path[:0] = [str(ROOT / "flashattention-pytorch_b200"), str(ROOT)]
 
 def stage_probe(mode, dtype_name):
     import torch
-    import flashattention_lab_cuda as ext
+    import probes
 
     dt = getattr(torch, dtype_name)
     torch.manual_seed(mode)
     a = torch.randn(256 if mode >= 4 else 128, 128, device="cuda", dtype=dt)
     b = torch.randn(128, 128, device="cuda", dtype=dt)
-    out = ext.probe_umma(mode, a, b)
+    out = probes.probe_umma(mode, a, b)
     torch.cuda.synchronize()
     af, bf = a.float(), b.float()
     want = {0: lambda: af @ bf.T, 1: lambda: af @ bf, 2: lambda: af @ bf, 3: lambda: af.T @ bf,

@@ -16,7 +16,7 @@ sys.path[:0] = [str(ROOT / "flashattention-pytorch_b200"), str(ROOT)]
 
 def stage_rate(mma=True):
     import torch
-    import flashattention_lab_cuda as ext
+    import probes
 
     sms = torch.cuda.get_device_properties(0).multi_processor_count
     ctas = sms - (sms & 1)
@@ -28,13 +28,13 @@ def stage_rate(mma=True):
     ]
     for pair, ts, n in (configs if mma else []):
         for _ in range(2):
-            ext.probe_mma_rate(pair, ts, n, 256, ctas)
+            probes.probe_mma_rate(pair, ts, n, 256, ctas)
         torch.cuda.synchronize()
         best = None
         for _ in range(3):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            ext.probe_mma_rate(pair, ts, n, groups, ctas)
+            probes.probe_mma_rate(pair, ts, n, groups, ctas)
             e1.record()
             torch.cuda.synchronize()
             ms = e0.elapsed_time(e1)
@@ -50,11 +50,11 @@ def stage_rate(mma=True):
         acc = torch.zeros(slices, nqt * 128, 128, device="cuda", dtype=torch.float32)
         n_calls = 0
         for flags in (0, 1, 4, 2, 3, 6):
-            ext.probe_reduce_rate(acc, nkt, flags)
+            probes.probe_reduce_rate(acc, nkt, flags)
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            ext.probe_reduce_rate(acc, nkt, flags)
+            probes.probe_reduce_rate(acc, nkt, flags)
             e1.record()
             torch.cuda.synchronize()
             n_calls += 2

@@ -1,23 +1,80 @@
-"""BASELINE config C3: FA1 and FA3 entry points, fwd / bwd / fwd+bwd sweep over N in {1K..16K}, d in {64,128},
-fp16/bf16, causal and non-causal, constant 16K tokens and hidden size 2048 (B = 16384/N, H = 2048/d), as the
-reference's benchmark conventions (benchmarks/bench_utils.py:83-97: seed 0, q,k,v,dO = randn) prescribe.
-Prints a markdown table + one JSON line per point.  Timing: CUDA events, 3 warm-up + 10 timed calls per point."""
+"""Benchmark sweep in the reference's harness conventions: the CLI flags of
+`benchmarks/bench_utils.py:250-264` (add_common_args), records in the `BenchmarkRecord` schema (`:161-180`) written as
+JSON + CSV with the field order of `write_results` (`:287-325`), so the reference's plotting loads them unchanged —
+over the FA1 / FA2 / FA3 entry points like `benchmarks/bench_compare_all.py`.
+
+    python tools/sweep.py --c3                     # BASELINE config C3: fa1+fa3, N 1K..16K, d 64/128, fp16/bf16,
+                                                   # constant 16K tokens and hidden 2048 (B = 16384/N, H = 2048/d)
+    python tools/sweep.py --algos fa1 fa2 fa3 --seqlen 512 1024 --head-dim 64 128 256 --batch-size 1 2 --num-heads 4
+
+Timing: CUDA events around every call (the reference uses perf_counter + synchronize, `:128-132`), `--warmup` untimed
+and `--iters` timed calls per point; inputs as `bench_utils.py:83-97` (seed 0; q, k, v, then dO from one generator).
+`tflops` follows the reference's convention (forward 4*B*H*N^2*D, "backward" = fwd+bwd time with 8*B*H*N^2*D, no
+causal discount, `:210-215`); the algorithmic rate (14*B*H*N^2*D*(1/2 if causal) for fwd+bwd) goes into `config`."""
+import argparse
+import csv
 import json
 import sys
 from pathlib import Path
 
 ROOT = Path(__file__).resolve().parents[1]
 sys.path[:0] = [str(ROOT / "flashattention-pytorch_b200"), str(ROOT)]
-import torch
-from fa1 import fa1_attention
-from fa3 import fa3_attention
 
+# reference benchmarks/bench_utils.py:161-180 (dataclass fields) == the CSV header of write_results (:300-319)
+REF_FIELDS = ["method", "algo", "backend", "direction", "dtype", "causal", "seqlen", "head_dim", "batch_size",
+              "num_heads", "mean_ms", "std_ms", "tflops", "peak_mem_mb", "status", "fp8", "config", "error"]
 NOMINAL = 2250.0
+DTYPES = {"fp16": "float16", "float16": "float16", "bf16": "bfloat16", "bfloat16": "bfloat16", "fp32": "float32",
+          "float32": "float32"}
 
 
-def timeit(fn, iters=10, stats=None):
-    """mean ms per call; per-call CUDA events so a std can be reported like the reference's benchmark_fn."""
-    for _ in range(3):
+def add_common_args(parser):  # reference benchmarks/bench_utils.py:250-264, same flags and defaults
+    parser.add_argument("--device", default="cuda", choices=["cpu", "cuda"])
+    parser.add_argument("--seqlen", type=int, nargs="+", default=[512, 1024, 2048, 4096, 8192, 16384])
+    parser.add_argument("--head-dim", type=int, nargs="+", default=[64, 128, 256])
+    parser.add_argument("--batch-size", type=int, nargs="+", default=[1, 2])
+    parser.add_argument("--num-heads", type=int, nargs="+", default=[4])
+    parser.add_argument("--causal", action="store_true", help="Run only causal mode (defaults to both)")
+    parser.add_argument("--non-causal-only", action="store_true", help="Run only non-causal mode")
+    parser.add_argument("--dtypes", type=str, nargs="+", default=["fp16", "bf16"], help="Dtypes: fp16 bf16 fp32")
+    parser.add_argument("--warmup", type=int, default=5)
+    parser.add_argument("--iters", type=int, default=20)
+
+
+def iter_causal_flags(args):  # reference benchmarks/bench_utils.py:267-272
+    if args.causal:
+        return [True]
+    if args.non_causal_only:
+        return [False]
+    return [False, True]
+
+
+def make_record(algo, direction, dtype, causal, n, d, b, h, mean_ms, std_ms, peak_mb, status="ok", error=None,
+                algorithmic_tflops=None):
+    """One row in the reference's BenchmarkRecord schema."""
+    factor = 4.0 if direction == "forward" else 8.0  # reference attention_flops (:210-215)
+    tflops = None if mean_ms is None else factor * b * h * n * n * d / (mean_ms * 1e-3) / 1e12
+    return {"method": f"{algo.upper()} (sm_100a)", "algo": algo, "backend": "cuda", "direction": direction,
+            "dtype": dtype, "causal": bool(causal), "seqlen": n, "head_dim": d, "batch_size": b, "num_heads": h,
+            "mean_ms": mean_ms, "std_ms": std_ms, "tflops": tflops, "peak_mem_mb": peak_mb, "status": status,
+            "fp8": False if algo == "fa3" else None,
+            "config": None if algorithmic_tflops is None else f"algorithmic_tflops={algorithmic_tflops:.1f}",
+            "error": error}
+
+
+def write_results(name, records, out_dir):
+    out_dir.mkdir(parents=True, exist_ok=True)
+    (out_dir / f"{name}.json").write_text(json.dumps(records, indent=2))
+    with (out_dir / f"{name}.csv").open("w", newline="") as f:
+        w = csv.DictWriter(f, fieldnames=REF_FIELDS)
+        w.writeheader()
+        w.writerows(records)
+
+
+def timeit(fn, warmup, iters):
+    import torch
+
+    for _ in range(warmup):
         fn()
     torch.cuda.synchronize()
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
@@ -28,73 +85,83 @@ def timeit(fn, iters=10, stats=None):
     torch.cuda.synchronize()
     ts = [a.elapsed_time(b) for a, b in evs]
     mean = sum(ts) / len(ts)
-    if stats is not None:
-        stats["std"] = (sum((t - mean) ** 2 for t in ts) / len(ts)) ** 0.5
-    return mean
+    return mean, (sum((t - mean) ** 2 for t in ts) / len(ts)) ** 0.5
 
 
-# Records in the reference's own schema (benchmarks/bench_utils.py:161-207 BenchmarkRecord; :210-215 FLOP convention:
-# forward 4*B*H*N^2*D, "backward" 8*B*H*N^2*D for the fwd+bwd time, NO causal discount) so its plotting can load them.
-REF_FIELDS = ["method", "algo", "backend", "direction", "dtype", "causal", "seqlen", "head_dim", "batch_size",
-              "num_heads", "mean_ms", "std_ms", "tflops", "peak_mem_mb", "status", "fp8", "config", "error"]
-ref_records = []
+def run_point(api_name, api, dtype_name, d, n, b, h, causal, warmup, iters):
+    import torch
+
+    dtype = getattr(torch, DTYPES[dtype_name])
+    g = torch.Generator(device="cuda").manual_seed(0)
+    q, k, v = (torch.randn((b, h, n, d), generator=g, device="cuda", dtype=dtype).requires_grad_(True) for _ in range(3))
+    do = torch.randn((b, h, n, d), generator=g, device="cuda", dtype=dtype)
+    f_fwd = 4.0 * b * h * n * n * d * (0.5 if causal else 1.0)
+    torch.cuda.reset_peak_memory_stats()
+    with torch.no_grad():
+        t_f, sd_f = timeit(lambda: api(q, k, v, causal=causal, backend="cuda"), warmup, iters)
+    o, _ = api(q, k, v, causal=causal, backend="cuda")
+
+    def bwd():
+        torch.autograd.backward(o, do, retain_graph=True)
+        q.grad = k.grad = v.grad = None
+
+    t_b, sd_b = timeit(bwd, warmup, iters)
+    peak_mb = torch.cuda.max_memory_allocated() / 2 ** 20
+    row = {"api": api_name, "dtype": dtype_name, "d": d, "N": n, "B": b, "H": h, "causal": causal, "fwd_ms": t_f,
+           "bwd_ms": t_b, "fwd_tflops": f_fwd / t_f / 1e9, "bwd_tflops": 2.5 * f_fwd / t_b / 1e9,
+           "fwd_bwd_tflops": 3.5 * f_fwd / (t_f + t_b) / 1e9}
+    row["frac_nominal"] = row["fwd_bwd_tflops"] / NOMINAL
+    recs = [make_record(api_name, "forward", dtype_name, causal, n, d, b, h, t_f, sd_f, peak_mb,
+                        algorithmic_tflops=row["fwd_tflops"]),
+            make_record(api_name, "backward", dtype_name, causal, n, d, b, h, t_f + t_b, (sd_f ** 2 + sd_b ** 2) ** 0.5,
+                        peak_mb, algorithmic_tflops=row["fwd_bwd_tflops"])]
+    return row, recs
 
 
-def ref_record(api_name, direction, dtype, causal, n, d, b, h, mean_ms, std_ms, peak_mb, algo_tflops):
-    factor = 4.0 if direction == "forward" else 8.0
-    ref_records.append({
-        "method": f"{api_name.upper()} (sm_100a)", "algo": api_name, "backend": "cuda", "direction": direction,
-        "dtype": dtype, "causal": bool(causal), "seqlen": n, "head_dim": d, "batch_size": b, "num_heads": h,
-        "mean_ms": mean_ms, "std_ms": std_ms, "tflops": factor * b * h * n * n * d / (mean_ms * 1e-3) / 1e12,
-        "peak_mem_mb": peak_mb, "status": "ok", "fp8": False if api_name == "fa3" else None,
-        "config": f"algorithmic_tflops={algo_tflops:.1f}", "error": None})
+def main():
+    ap = argparse.ArgumentParser(description=__doc__, formatter_class=argparse.RawDescriptionHelpFormatter)
+    add_common_args(ap)
+    ap.add_argument("--algos", nargs="+", default=["fa1", "fa2", "fa3"], choices=["fa1", "fa2", "fa3"])
+    ap.add_argument("--c3", action="store_true", help="BASELINE config C3 preset (overrides shapes / dtypes / algos)")
+    ap.add_argument("--out", default=str(ROOT / "gpurun_out"), help="directory for <name>.json / <name>.csv")
+    ap.add_argument("--name", default="sweep_records")
+    args = ap.parse_args()
+    import torch
+    from fa1 import fa1_attention
+    from fa2 import fa2_attention
+    from fa3 import fa3_attention
+
+    apis = {"fa1": fa1_attention, "fa2": fa2_attention, "fa3": fa3_attention}
+    if args.c3:
+        points = [(a, dt, d, n, 16384 // n, 2048 // d, c) for a in ("fa1", "fa3") for dt in ("bf16", "fp16")
+                  for d in (128, 64) for n in (1024, 2048, 4096, 8192, 16384) for c in (True, False)]
+        warmup, iters = 3, 10
+    else:
+        points = [(a, dt, d, n, b, h, c) for a in args.algos for dt in args.dtypes for d in args.head_dim
+                  for n in args.seqlen for b in args.batch_size for h in args.num_heads for c in iter_causal_flags(args)]
+        warmup, iters = args.warmup, args.iters
+    rows, records = [], []
+    print("| api | dtype | d | N | B | H | causal | fwd ms | fwd TF/s | bwd ms | bwd TF/s | fwd+bwd TF/s | % of 2250 |")
+    print("|---|---|---|---|---|---|---|---|---|---|---|---|---|")
+    for api_name, dt, d, n, b, h, causal in points:
+        try:
+            row, recs = run_point(api_name, apis[api_name], dt, d, n, b, h, causal, warmup, iters)
+        except (NotImplementedError, RuntimeError) as exc:  # unsupported point: recorded like the reference does
+            oom = "out of memory" in str(exc).lower()
+            status = "oom" if oom else "unsupported"
+            records += [make_record(api_name, direction, dt, causal, n, d, b, h, None, None, None, status, str(exc)[:200])
+                        for direction in ("forward", "backward")]
+            print(f"| {api_name} | {dt} | {d} | {n} | {b} | {h} | {causal} | - | - | - | - | {status} | - |", flush=True)
+            torch.cuda.empty_cache()
+            continue
+        rows.append(row)
+        records += recs
+        print(f"| {api_name} | {dt} | {d} | {n} | {b} | {h} | {causal} | {row['fwd_ms']:.3f} | {row['fwd_tflops']:.0f} | "
+              f"{row['bwd_ms']:.3f} | {row['bwd_tflops']:.0f} | {row['fwd_bwd_tflops']:.0f} | "
+              f"{100 * row['frac_nominal']:.1f} |", flush=True)
+    print("JSON " + json.dumps(rows))
+    write_results(args.name, records, Path(args.out))
 
 
-rows = []
-print("| api | dtype | d | N | causal | fwd ms | fwd TF/s | bwd ms | bwd TF/s | fwd+bwd TF/s | % of 2250 |")
-print("|---|---|---|---|---|---|---|---|---|---|---|")
-for api_name, api in (("fa1", fa1_attention), ("fa3", fa3_attention)):
-    for dtype in (torch.bfloat16, torch.float16):
-        for d in (128, 64):
-            for n in (1024, 2048, 4096, 8192, 16384):
-                for causal in (True, False):
-                    b, h = 16384 // n, 2048 // d
-                    g = torch.Generator(device="cuda").manual_seed(0)
-                    q, k, v = (torch.randn((b, h, n, d), generator=g, device="cuda", dtype=dtype).requires_grad_(True)
-                               for _ in range(3))
-                    do = torch.randn((b, h, n, d), generator=g, device="cuda", dtype=dtype)
-                    c = 0.5 if causal else 1.0
-                    f_fwd = 4.0 * b * h * n * n * d * c
-                    torch.cuda.reset_peak_memory_stats()
-                    st_f, st_b = {}, {}
-                    with torch.no_grad():
-                        t_f = timeit(lambda: api(q, k, v, causal=causal, backend="cuda"), stats=st_f)
-                    o, _ = api(q, k, v, causal=causal, backend="cuda")
-
-                    def bwd():
-                        torch.autograd.backward(o, do, retain_graph=True)
-                        q.grad = k.grad = v.grad = None
-
-                    t_b = timeit(bwd, stats=st_b)
-                    peak_mb = torch.cuda.max_memory_allocated() / 2 ** 20
-                    tf_f, tf_b = f_fwd / t_f / 1e9, 2.5 * f_fwd / t_b / 1e9
-                    tf_fb = 3.5 * f_fwd / (t_f + t_b) / 1e9
-                    rec = {"api": api_name, "dtype": str(dtype).split(".")[-1], "d": d, "N": n, "B": b, "H": h,
-                           "causal": causal, "fwd_ms": t_f, "bwd_ms": t_b, "fwd_tflops": tf_f, "bwd_tflops": tf_b,
-                           "fwd_bwd_tflops": tf_fb, "frac_nominal": tf_fb / NOMINAL}
-                    rows.append(rec)
-                    dn = str(dtype).split(".")[-1]
-                    ref_record(api_name, "forward", dn, causal, n, d, b, h, t_f, st_f["std"], peak_mb, f_fwd / t_f / 1e9)
-                    ref_record(api_name, "backward", dn, causal, n, d, b, h, t_f + t_b, (st_f["std"] ** 2 + st_b["std"] ** 2) ** 0.5,
-                               peak_mb, 3.5 * f_fwd / (t_f + t_b) / 1e9)
-                    print(f"| {api_name} | {rec['dtype']} | {d} | {n} | {causal} | {t_f:.3f} | {tf_f:.0f} | {t_b:.3f} | "
-                          f"{tf_b:.0f} | {tf_fb:.0f} | {100 * tf_fb / NOMINAL:.1f} |", flush=True)
-print("JSON " + json.dumps(rows))
-out = ROOT / "gpurun_out"
-out.mkdir(exist_ok=True)
-(out / "sweep_records.json").write_text(json.dumps(ref_records, indent=2))
-import csv
-with (out / "sweep_records.csv").open("w", newline="") as f:
-    w = csv.DictWriter(f, fieldnames=REF_FIELDS)
-    w.writeheader()
-    w.writerows(ref_records)
+if __name__ == "__main__":
+    main()
