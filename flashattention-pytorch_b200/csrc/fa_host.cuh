@@ -111,6 +111,35 @@ inline int sched_group_log2(bool skewed, long long n_ranks, long long n_slices) 
   while ((2ll << lg) <= g && (2ll << lg) <= n_slices) ++lg;  // largest power of two <= min(g, n_slices)
   return lg;
 }
+// Persistent grids: one CTA per SM, minus `sm_margin` SMs left free for concurrently running communication kernels
+// (NCCL send/recv in the ring-attention schedule cannot make progress under 148 resident one-CTA-per-SM kernels).
+// The margin is process-wide state set through fa_sm100_set_sm_margin() or the FA_SM100_SM_MARGIN environment variable.
+inline int& sm_margin_ref() {
+  static int margin = [] {
+    const char* e = std::getenv("FA_SM100_SM_MARGIN");
+    const int v = e ? std::atoi(e) : 0;
+    return v > 0 ? v : 0;
+  }();
+  return margin;
+}
+inline long long persistent_ctas(long long n_items) {
+  static const bool one_item_per_cta = [] {  // FA_SM100_PERSISTENT=0: measurement knob, one CTA per work item
+    const char* e = std::getenv("FA_SM100_PERSISTENT");
+    return e != nullptr && e[0] == '0';
+  }();
+  if (one_item_per_cta) return n_items;
+  static int sms[64];  // per device; benign race: idempotent writes
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+  int n = (dev >= 0 && dev < 64) ? sms[dev] : 0;
+  if (n == 0) {
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return -1;
+    if (dev >= 0 && dev < 64) sms[dev] = n;
+  }
+  long long ctas = n - sm_margin_ref();
+  if (ctas < 1) ctas = 1;
+  return n_items < ctas ? n_items : ctas;
+}
 inline int launch_status() { return cudaGetLastError() == cudaSuccess ? FA_SM100_OK : FA_SM100_ELAUNCH; }
 
 }  // namespace fa

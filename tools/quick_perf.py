@@ -45,7 +45,10 @@ def time_ms(fn, iters=10):
 
 def perf():
     d = 128
-    for (bh, n, causal) in ((64, 4096, True), (64, 8192, False), (64, 8192, True)):
+    shapes = ((256, 1024, True), (128, 2048, True), (64, 4096, True), (64, 8192, False), (64, 8192, True))
+    if "--short" in sys.argv:
+        shapes = shapes[2:]
+    for (bh, n, causal) in shapes:
         torch.manual_seed(0)
         q, k, v, do = (torch.randn(bh, n, d, device="cuda", dtype=torch.bfloat16) for _ in range(4))
         o, lse = ext.fwd_raw(q, k, v, causal, d ** -0.5)
@@ -55,7 +58,11 @@ def perf():
             print(f"bh={bh} n={n} causal={int(causal)}: fwd {t_f:.3f} ms {flops_f / t_f / 1e9:7.1f} TFLOP/s", flush=True)
             continue
         t_b = time_ms(lambda: ext.bwd_raw(q, k, v, o, do, lse, causal, d ** -0.5))
+        acc = torch.empty(bh, n, d, device="cuda", dtype=torch.float32)
+        stats = ext.bwd_prepare_raw(o, do, lse, zero=acc)
+        t_m = time_ms(lambda: ext.bwd_raw(q, k, v, None, do, None, causal, d ** -0.5, rowstats=stats, dq_accum=acc))
         print(f"bh={bh} n={n} causal={int(causal)}: fwd {t_f:.3f} ms {flops_f / t_f / 1e9:7.1f} TFLOP/s | "
+              f"bwd kernel {t_m:.3f} ms {2.5 * flops_f / t_m / 1e9:7.1f} | "
               f"bwd(all launches) {t_b:.3f} ms {2.5 * flops_f / t_b / 1e9:7.1f} TFLOP/s | "
               f"fwd+bwd {3.5 * flops_f / (t_f + t_b) / 1e9:7.1f} TFLOP/s", flush=True)
 
