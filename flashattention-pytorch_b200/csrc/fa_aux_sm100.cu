@@ -72,6 +72,7 @@ extern "C" const char* fa_sm100_strerror(int code) {
     case FA_SM100_EDRIVER: return "cuTensorMapEncodeTiled unavailable or failed";
     case FA_SM100_ELAUNCH: return "CUDA kernel launch failed";
     case FA_SM100_EDEVICE: return "current CUDA device is not sm_100";
+    case FA_SM100_EINVAL_EXT: return "bad extras (dropout_p outside [0,1), offsets not multiples of 4, or too many tiles for the mask)";
     default: return "unknown fa_sm100 error";
   }
 }

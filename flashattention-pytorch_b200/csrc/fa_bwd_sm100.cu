@@ -25,33 +25,38 @@
 #include "fa_host.cuh"
 
 // Optional per-phase timeline of one CTA (build with -DFA_BWD_TRACE; tools/bwd_trace.py reads it back).  clock64 is
-// the SM's cycle counter, so all warps of the traced CTA share one time base.  Events are indexed by the CTA's running
-// query-tile count, so the trace shows item boundaries (epilogue / next item's prologue) as well.
+// the SM's cycle counter, so all warps of the traced CTA share one time base.
 #ifdef FA_BWD_TRACE
 #ifndef FA_BWD_TRACE_ITERS
-#define FA_BWD_TRACE_ITERS 128
+#define FA_BWD_TRACE_ITERS 64
 #endif
-#define FA_BWD_TRACE_EVENTS 20
+#define FA_BWD_TRACE_EVENTS 16
 __device__ long long fa_bwd_trace_buf[FA_BWD_TRACE_EVENTS * FA_BWD_TRACE_ITERS];
-__device__ long long fa_bwd_span_buf[2 * 256];  // wall-clock entry / exit of every (persistent) CTA
 __device__ int fa_bwd_trace_block = 0;
+__device__ __forceinline__ int fa_bwd_lin_block() {
+  return static_cast<int>(blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z));
+}
+#define FA_TRACE(ev, it)                                                                       \
+  do {                                                                                         \
+    if (fa_bwd_lin_block() == fa_bwd_trace_block && (it) < FA_BWD_TRACE_ITERS)                 \
+      fa_bwd_trace_buf[(ev) * FA_BWD_TRACE_ITERS + (it)] = clock64();                          \
+  } while (0)
+// per-CTA lifetime stamps of EVERY CTA (8 values each): SM id, wall-clock entry/exit, cycle stamps of the boundaries
+#define FA_BWD_LIFE_MAX_CTAS 16384
+__device__ long long fa_bwd_life_buf[FA_BWD_LIFE_MAX_CTAS * 8];
 __device__ __forceinline__ long long fa_bwd_globaltimer() {
   long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
-#define FA_SPAN(slot)                                                                          \
+#define FA_LIFE(slot, value)                                                                   \
   do {                                                                                         \
-    if (threadIdx.x == 0 && blockIdx.x < 256) fa_bwd_span_buf[2 * blockIdx.x + (slot)] = fa_bwd_globaltimer(); \
-  } while (0)
-#define FA_TRACE(ev, it)                                                                       \
-  do {                                                                                         \
-    if (static_cast<int>(blockIdx.x) == fa_bwd_trace_block && (it) < FA_BWD_TRACE_ITERS)       \
-      fa_bwd_trace_buf[(ev) * FA_BWD_TRACE_ITERS + (it)] = clock64();                          \
+    const int lin_ = fa_bwd_lin_block();                                                       \
+    if (lin_ < FA_BWD_LIFE_MAX_CTAS) fa_bwd_life_buf[lin_ * 8 + (slot)] = (value);             \
   } while (0)
 #else
 #define FA_TRACE(ev, it) do { } while (0)
-#define FA_SPAN(slot) do { } while (0)
+#define FA_LIFE(slot, value) do { } while (0)
 #endif
 
 namespace fa {
@@ -60,15 +65,26 @@ struct BwdParams {
   const float* rowstats;  // (bh, nqt, 2, 128): -lse*log2e then -delta, per 128-row query tile
   float* dq_accum;        // fp32 dQ accumulator (bh, n_q, D) with slice stride dq_bh_stride (elements)
   long long dq_bh_stride;
-  long long n_items;      // work items = slice groups x kv tiles x slices per group (padding slices included)
   int n_q, n_kv, bh, causal, diag, nqt, nkt, group_log2;
   int d;  // true head dim (<= D); the tensor maps zero-fill / clip the columns in [d, D)
   int accum_kv;  // 0: dk / dv written in the input dtype   1: fp32 partials reduce-added into travelling accumulators
   float scale_log2, scale;
+  // ---- extended variant only (kExt): block-sparse tile mask and dropout (see fa_fwd_sm100.cu) ----
+  const uint8_t* block_mask;  // (nqt, nkt) per slice or shared, nonzero = tile is computed; nullable
+  long long mask_bh_stride;
+  uint32_t seed_lo, seed_hi, rng_offset;
+  uint32_t drop_threshold;    // an element is dropped iff its random byte < threshold (0: no dropout)
+  float drop_scale;
+  long long q_row0, kv_col0;  // global offsets for the random bits
 };
+constexpr int kMaxMaskTiles = 4096;  // extended variant: query tiles per slice the active-tile bitmap can hold
 
 constexpr int kBwdThreads = 480;  // 15 warps (16 x 128 registers does not launch: the register file has no slack)
 constexpr int kT = 128;  // tile edge (query rows and kv rows)
+#ifndef FA_GRID_Y_BITS
+#define FA_GRID_Y_BITS 15  // grid.y carries up to 2^15 kv tiles; larger indices fold into grid.x.  Tests build with 2 to
+#endif                     // exercise the folding at small sizes (tools/README.md)
+constexpr int kRankBitsY = FA_GRID_Y_BITS;
 
 template <int D>
 struct BwdCfg {
@@ -80,7 +96,7 @@ struct BwdCfg {
   static constexpr int kOffV = kOffK + kTileBytes;
   static constexpr int kOffQ = kOffV + kTileBytes;        // 2 stages
   static constexpr int kOffDO = kOffQ + 2 * kTileBytes;   // 2 stages
-  static constexpr int kOffDS = kOffDO + 2 * kTileBytes;  // dS^T tile; doubles as the dK/dV write-out staging
+  static constexpr int kOffDS = kOffDO + 2 * kTileBytes;  // dS^T tile
   // dQ staging (2 x 16 KiB): at D = 128 there is no room left, so it borrows the (dead) dO stage of the tile being
   // drained; at D = 64 it has its own buffers
   static constexpr bool kStageInDO = (D == 128);
@@ -88,51 +104,20 @@ struct BwdCfg {
   static constexpr int kOffStats = kOffStage + (kStageInDO ? 0 : 2 * kDqStageBytes);  // 2 stages x 1 KiB
   static constexpr int kOffBars = kOffStats + 2 * 1024;
   static constexpr int kSmemBytes = kOffBars + 256;
+  static constexpr int kOffBitmap = kSmemBytes;  // extended variant: active query tiles of this K/V tile, 1 bit each
+  static constexpr int kSmemBytesExt = kOffBitmap + kMaxMaskTiles / 8 + 16;
 };
-static_assert(BwdCfg<128>::kSmemBytes <= 232448, "backward smem budget");
+static_assert(BwdCfg<128>::kSmemBytesExt <= 232448, "backward smem budget");
 
 enum BwdBar : int {
   kBarKV = 0, kBarQFull0, kBarQFull1, kBarQEmpty0, kBarQEmpty1, kBarDOFull0, kBarDOFull1, kBarDOEmpty0, kBarDOEmpty1,
   kBarSFull, kBarDPFull, kBarDPIssued, kBarPReady, kBarDSHalf, kBarDSReady, kBarDQFull, kBarDQDrained, kBarStageFree0, kBarStageFree1,
-  kBarDKVDone, kBarAccFree, kBarCount
+  kBarDKVDone, kBarCount
 };
 
-// One unit of work: a 128-row K/V tile of one slice and the query tiles that see it.
-struct BwdItem {
-  int bh, j, i_min, n_iter;
-  bool valid;  // false: padding (slice index past the end, or past the last item) -- nothing to do at all
-};
-
-// The k-th item of this (persistent) CTA.  Items are numbered in the LPT order described in ptx.cuh -- slice groups
-// outermost, then kv tile (ascending = heaviest first under the causal mask), then the slice inside its group -- and
-// dealt to the CTAs in "snake" order (round k runs left to right for even k, right to left for odd k), which pairs
-// every CTA's heavier items with lighter ones when the cost falls monotonically along the order.
-__device__ __forceinline__ BwdItem bwd_item(const BwdParams& p, int k) {
-  const long long G = gridDim.x;
-  const long long w = k * G + ((k & 1) ? (G - 1 - static_cast<long long>(blockIdx.x)) : static_cast<long long>(blockIdx.x));
-  BwdItem it;
-  it.valid = w < p.n_items;
-  const unsigned t = static_cast<unsigned>(w >> p.group_log2);
-  const unsigned z = t / static_cast<unsigned>(p.nkt);
-  it.j = static_cast<int>(t - z * static_cast<unsigned>(p.nkt));
-  it.bh = static_cast<int>((z << p.group_log2) + (static_cast<unsigned>(w) & ((1u << p.group_log2) - 1u)));
-  if (it.bh >= p.bh) it.valid = false;
-  it.i_min = 0;
-  if (p.causal) {
-    const int first = it.j * kT - p.diag;  // first query row that sees this tile's first key
-    it.i_min = first > 0 ? first / kT : 0;
-  }
-  it.n_iter = (it.valid && p.nqt > it.i_min) ? p.nqt - it.i_min : 0;
-  return it;
-}
-
-// Persistent kernel: gridDim.x CTAs (one per SM, minus an optional margin left to communication kernels) each walk
-// their items back to back.  TMEM, the barriers and the Q/dO rings are set up once; the rings and every per-tile
-// barrier simply keep running across item boundaries (`gt` = the CTA's running query-tile count gives stage and
-// phase), so the next item's K/V/Q/dO loads, S^T and dP^T products overlap the current item's last dQ drain and its
-// dK/dV write-out.  Per-item barriers (K/V landed, dK/dV complete, accumulators free again) are phased by `act`, the
-// running count of items that had work.
-template <int D, bool kBF16>
+// kExt = true: block-sparse tile mask (inactive query tiles of this K/V tile are skipped by every role) and dropout
+// (same Philox bits as the forward); kExt = false is the dense kernel.
+template <int D, bool kBF16, bool kExt>
 __global__ void __launch_bounds__(kBwdThreads, 1)
 fa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
               const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_do,
@@ -154,17 +139,86 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
 
   const int warp = static_cast<int>(warp_uniform(threadIdx.x >> 5));
   const int lane = threadIdx.x & 31;
-  const int n_rounds = static_cast<int>((p.n_items + gridDim.x - 1) / gridDim.x);  // items per CTA (tail: padding)
-  FA_SPAN(0);
+
+  // Work-item order through the grid shape (see the note on work-item order in ptx.cuh; no division in the kernel): x = slice inside
+  // its group (fastest), y = kv tile j (ascending = heaviest first under the causal mask), z = slice group; tile
+  // indices beyond the y limit of a grid are folded into x above the slice bits.
+  const int j = static_cast<int>(((blockIdx.x >> p.group_log2) << kRankBitsY) + blockIdx.y);
+  const int bh = static_cast<int>((blockIdx.z << p.group_log2) + (blockIdx.x & ((1u << p.group_log2) - 1u)));
+  if (bh >= p.bh || j >= p.nkt) return;  // padding of the last group / folded tile indices
+#ifdef FA_BWD_TRACE
+  if (threadIdx.x == 0) {
+    uint32_t smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    FA_LIFE(0, static_cast<long long>(smid));
+    FA_LIFE(1, fa_bwd_globaltimer());
+    FA_LIFE(2, clock64());
+  }
+#endif
+  int i_min = 0;
+  if (p.causal) {
+    const int first = j * kT - p.diag;  // first query row that sees this tile's first key
+    i_min = first > 0 ? first / kT : 0;
+  }
+  int n_iter = p.nqt > i_min ? p.nqt - i_min : 0;
+  // Query tiles are walked in ascending order.  Dense: i_min, i_min + 1, ...  Sparse (kExt with a block mask): the
+  // set bits of a bitmap built below; every role keeps its own cursor and steps it with next_tile().
+  const bool sparse = kExt && p.block_mask != nullptr;
+  uint32_t* act_bits = reinterpret_cast<uint32_t*>(smem + Cfg::kOffBitmap);  // kExt only
+  int* act_count = reinterpret_cast<int*>(smem + Cfg::kOffBitmap + kMaxMaskTiles / 8);
+  auto next_tile = [&](int i) -> int {  // smallest active tile index > i (p.nqt if none)
+    if (!sparse) return i + 1;
+    ++i;
+    while (i < p.nqt) {
+      const uint32_t w = act_bits[i >> 5] >> (i & 31);
+      if (w) return i + __ffs(w) - 1;
+      i = (i | 31) + 1;
+    }
+    return p.nqt;
+  };
+  if constexpr (kExt) {
+    if (sparse && warp == 12) {  // the producer warp builds the bitmap before anything is loaded
+      const uint8_t* col = p.block_mask + static_cast<long long>(bh) * p.mask_bh_stride + j;
+      int cnt = 0;
+      for (int base = 0; base < p.nqt; base += 32) {
+        const int i = base + lane;
+        const bool on = i >= i_min && i < p.nqt && col[static_cast<long long>(i) * p.nkt] != 0;
+        const uint32_t bits = __ballot_sync(0xffffffffu, on);
+        if (lane == 0) act_bits[base >> 5] = bits;
+        cnt += __popc(bits);
+      }
+      if (lane == 0) *act_count = cnt;
+      __syncwarp();
+      n_iter = cnt;
+    }
+  }
+  int first_tile = next_tile(i_min - 1);  // sparse: only the producer warp may trust the bitmap before the block sync
 
   if (threadIdx.x == 0 && (smem_u32(smem) & 1023u)) {
     printf("fa_sm100 bwd: dynamic smem base not 1024-aligned\n");
     __trap();
   }
+  // loads of one query tile (Q + row statistics on q_full, dO on do_full)
+  auto issue_q_tile = [&](int it, int i) {
+    const int st = it & 1;
+    mbar_arrive_expect_tx(&bars[kBarQFull0 + st], Cfg::kTileBytes + 1024);
+    for (int c = 0; c < kChunks; ++c)
+      tma_load_3d(q_smem + st * Cfg::kTileBytes + c * kSub, &tm_q, &bars[kBarQFull0 + st], c * 64, i * kT, bh);
+    bulk_load_1d(stats_smem + st * 256, p.rowstats + (static_cast<long long>(bh) * p.nqt + i) * 256, 1024,
+                 &bars[kBarQFull0 + st]);
+  };
+  auto issue_do_tile = [&](int it, int i) {
+    const int st = it & 1;
+    mbar_arrive_expect_tx(&bars[kBarDOFull0 + st], Cfg::kTileBytes);
+    for (int c = 0; c < kChunks; ++c)
+      tma_load_3d(do_smem + st * Cfg::kTileBytes + c * kSub, &tm_do, &bars[kBarDOFull0 + st], c * 64, i * kT, bh);
+  };
+  // The producer lane initialises the barriers and starts K, V and the first two query tiles BEFORE the block-wide
+  // sync, so their TMA latency overlaps the TMEM allocation and the rest of the prologue.
   if (warp == 12 && lane == 0) {
     for (int b = 0; b < kBarCount; ++b) {
       uint32_t count = 1u;
-      if (b == kBarPReady || b == kBarDSReady || b == kBarDSHalf || b == kBarAccFree) count = 256u;
+      if (b == kBarPReady || b == kBarDSReady || b == kBarDSHalf) count = 256u;
       if (b == kBarDQDrained) count = 128u;
       // operands shared by both MMA streams are released by two commits
       if (b == kBarQEmpty0 || b == kBarQEmpty1 || b == kBarDOEmpty0 || b == kBarDOEmpty1 || b == kBarDKVDone)
@@ -177,8 +231,15 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
     tma_prefetch_desc(&tm_v);
     tma_prefetch_desc(&tm_do);
     tma_prefetch_desc(&tm_dq);
-    tma_prefetch_desc(&tm_dk);
-    tma_prefetch_desc(&tm_dv);
+    mbar_arrive_expect_tx(&bars[kBarKV], 2 * Cfg::kTileBytes);
+    for (int c = 0; c < kChunks; ++c) {
+      tma_load_3d(k_smem + c * kSub, &tm_k, &bars[kBarKV], c * 64, j * kT, bh);
+      tma_load_3d(v_smem + c * kSub, &tm_v, &bars[kBarKV], c * 64, j * kT, bh);
+    }
+    for (int it = 0, i = first_tile; it < n_iter && it < 2; ++it, i = next_tile(i)) {
+      issue_q_tile(it, i);
+      issue_do_tile(it, i);
+    }
   }
   if (warp == 13) {
     tmem_alloc(tmem_slot, 512);
@@ -189,89 +250,45 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
   tc_fence_after();
   const uint32_t tmem_base = warp_uniform(*tmem_slot);
   constexpr uint32_t kColST = 0, kColDPT = 128, kColDV = 256, kColDK = 256 + D;
+  if constexpr (kExt) {
+    if (sparse) {  // bitmap and count were written by the producer warp before the block-wide sync
+      n_iter = *act_count;
+      first_tile = next_tile(i_min - 1);
+    }
+  }
 
   if (warp == 12) {
     // ===================================== TMA producer =====================================
-    if (lane == 0) {
-      // Three independent load sequences, each walking the CTA's items in order: K/V (one per item, once the previous
-      // item's products have finished with the buffers), Q + row statistics, and dO (one per query tile, as their ring
-      // stages free up).  Q(it) frees after dK(it); dO(it) only after the dQ(it) reduce staged in it has been read --
-      // polling all three keeps a late stage of one kind from holding back the others, in particular the next
-      // item's first tiles, which are fetched while the current item is still draining.
-      int kv_round = 0, kv_act = 0;  // next item whose K/V are to be loaded; active items before it
-      BwdItem kv_item = bwd_item(p, 0);
-      int q_round = 0, q_it = 0, q_gt = 0;
-      BwdItem q_item = kv_item;
-      int do_round = 0, do_it = 0, do_gt = 0;
-      BwdItem do_item = kv_item;
-      auto skip_empty = [&](int& round, BwdItem& item) {
-        while (round < n_rounds && item.n_iter == 0) {
-          ++round;
-          if (round < n_rounds) item = bwd_item(p, round);
-        }
-      };
-      skip_empty(kv_round, kv_item);
-      skip_empty(q_round, q_item);
-      skip_empty(do_round, do_item);
+    if (lane == 0) {  // K, V and query tiles 0, 1 were issued in the prologue
+      // Q and dO stages free up at different moments (Q(it) after dK(it); dO(it) only after the dQ(it) reduce staged in
+      // it has been read), so the two load sequences advance independently: polling both keeps a late dO stage from
+      // holding back the next Q tile, which heads the following iteration's critical path.
+      int q_next = 2, do_next = 2;
+      int q_tile = next_tile(next_tile(first_tile)), do_tile = q_tile;  // third active tile (if any)
       const long long t0 = clock64();
-      while (kv_round < n_rounds || q_round < n_rounds || do_round < n_rounds) {
-        if (kv_round < n_rounds &&
-            (kv_act == 0 || mbar_test_wait(&bars[kBarDKVDone], (kv_act - 1) & 1))) {  // previous item is done with K, V
-          mbar_arrive_expect_tx(&bars[kBarKV], 2 * Cfg::kTileBytes);
-          for (int c = 0; c < kChunks; ++c) {
-            tma_load_3d(k_smem + c * kSub, &tm_k, &bars[kBarKV], c * 64, kv_item.j * kT, kv_item.bh);
-            tma_load_3d(v_smem + c * kSub, &tm_v, &bars[kBarKV], c * 64, kv_item.j * kT, kv_item.bh);
-          }
-          ++kv_act;
-          ++kv_round;
-          if (kv_round < n_rounds) kv_item = bwd_item(p, kv_round);
-          skip_empty(kv_round, kv_item);
+      while (q_next < n_iter || do_next < n_iter) {
+        if (q_next < n_iter && mbar_test_wait(&bars[kBarQEmpty0 + (q_next & 1)], ((q_next >> 1) & 1) ^ 1)) {
+          issue_q_tile(q_next, q_tile);
+          FA_TRACE(12, q_next);
+          ++q_next;
+          q_tile = next_tile(q_tile);
         }
-        if (q_round < n_rounds) {
-          const int st = q_gt & 1;
-          if (q_gt < 2 || mbar_test_wait(&bars[kBarQEmpty0 + st], ((q_gt >> 1) & 1) ^ 1)) {
-            const int i = q_item.i_min + q_it;
-            mbar_arrive_expect_tx(&bars[kBarQFull0 + st], Cfg::kTileBytes + 1024);
-            for (int c = 0; c < kChunks; ++c)
-              tma_load_3d(q_smem + st * Cfg::kTileBytes + c * kSub, &tm_q, &bars[kBarQFull0 + st], c * 64, i * kT,
-                          q_item.bh);
-            bulk_load_1d(stats_smem + st * 256, p.rowstats + (static_cast<long long>(q_item.bh) * p.nqt + i) * 256,
-                         1024, &bars[kBarQFull0 + st]);
-            FA_TRACE(12, q_gt);
-            ++q_gt;
-            if (++q_it == q_item.n_iter) {
-              q_it = 0;
-              ++q_round;
-              if (q_round < n_rounds) q_item = bwd_item(p, q_round);
-              skip_empty(q_round, q_item);
-            }
-          }
-        }
-        if (do_round < n_rounds) {
-          const int st = do_gt & 1;
-          const uint32_t par = ((do_gt >> 1) & 1) ^ 1;
-          bool ok = do_gt < 2 || mbar_test_wait(&bars[kBarDOEmpty0 + st], par);  // dV / dP of the previous user are done
-          if constexpr (Cfg::kStageInDO)                                          // ... and so is the dQ reduce staged there
-            ok = ok && (do_gt < 2 || mbar_test_wait(&bars[kBarStageFree0 + st], par));
+        if (do_next < n_iter) {
+          const uint32_t par = ((do_next >> 1) & 1) ^ 1;
+          bool ok = mbar_test_wait(&bars[kBarDOEmpty0 + (do_next & 1)], par);  // dV / dP of the previous user are done
+          if constexpr (Cfg::kStageInDO)                                        // ... and so is the dQ reduce staged there
+            ok = ok && mbar_test_wait(&bars[kBarStageFree0 + (do_next & 1)], par);
           if (ok) {
-            const int i = do_item.i_min + do_it;
-            mbar_arrive_expect_tx(&bars[kBarDOFull0 + st], Cfg::kTileBytes);
-            for (int c = 0; c < kChunks; ++c)
-              tma_load_3d(do_smem + st * Cfg::kTileBytes + c * kSub, &tm_do, &bars[kBarDOFull0 + st], c * 64, i * kT,
-                          do_item.bh);
-            FA_TRACE(13, do_gt);
-            ++do_gt;
-            if (++do_it == do_item.n_iter) {
-              do_it = 0;
-              ++do_round;
-              if (do_round < n_rounds) do_item = bwd_item(p, do_round);
-              skip_empty(do_round, do_item);
-            }
+            issue_do_tile(do_next, do_tile);
+            FA_TRACE(13, do_next);
+            ++do_next;
+            do_tile = next_tile(do_tile);
           }
         }
-        if (clock64() - t0 > 8 * FA_WAIT_TIMEOUT_CYCLES) {
-          printf("fa_sm100 bwd: producer timeout (block %d: kv round %d, q round %d tile %d, dO round %d tile %d of %d)\n",
-                 blockIdx.x, kv_round, q_round, q_it, do_round, do_it, n_rounds);
+        if (clock64() - t0 > FA_WAIT_TIMEOUT_CYCLES) {
+          printf("fa_sm100 bwd: producer timeout (block %d,%d,%d q_next %d, do_next %d of %d)\n", blockIdx.x, blockIdx.y,
+                 blockIdx.z, q_next, do_next,
+                 n_iter);
           __trap();
         }
       }
@@ -279,90 +296,81 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
     __syncwarp();
   } else if (warp == 13 || warp == 14) {
     // ===================================== MMA issuers (uniform control flow, one elected lane) ==================
-    constexpr uint32_t idesc_s = umma_idesc(kBF16, kT, kT, false, false);
-    constexpr uint32_t idesc_acc = umma_idesc(kBF16, kT, D, false, true);
-    constexpr uint32_t idesc_dq = umma_idesc(kBF16, kT, D, true, true);
-    constexpr uint32_t kSubLo = kSub >> 4, kTileLo = Cfg::kTileBytes >> 4;
-    // low descriptor words: K-major views (LBO unused = 16 B) and MN-major views (LBO = next 64-column sub-tile)
-    const uint32_t k_km = umma_desc_lo(smem_u32(k_smem), 16), v_km = umma_desc_lo(smem_u32(v_smem), 16);
-    const uint32_t q_km = umma_desc_lo(smem_u32(q_smem), 16), do_km = umma_desc_lo(smem_u32(do_smem), 16);
-    const uint32_t k_mn = umma_desc_lo(smem_u32(k_smem), kSub), q_mn = umma_desc_lo(smem_u32(q_smem), kSub);
-    const uint32_t do_mn = umma_desc_lo(smem_u32(do_smem), kSub), ds_mn = umma_desc_lo(smem_u32(ds_smem), kT * 128);
+    if (n_iter > 0) {
+      constexpr uint32_t idesc_s = umma_idesc(kBF16, kT, kT, false, false);
+      constexpr uint32_t idesc_acc = umma_idesc(kBF16, kT, D, false, true);
+      constexpr uint32_t idesc_dq = umma_idesc(kBF16, kT, D, true, true);
+      constexpr uint32_t kSubLo = kSub >> 4, kTileLo = Cfg::kTileBytes >> 4;
+      // low descriptor words: K-major views (LBO unused = 16 B) and MN-major views (LBO = next 64-column sub-tile)
+      const uint32_t k_km = umma_desc_lo(smem_u32(k_smem), 16), v_km = umma_desc_lo(smem_u32(v_smem), 16);
+      const uint32_t q_km = umma_desc_lo(smem_u32(q_smem), 16), do_km = umma_desc_lo(smem_u32(do_smem), 16);
+      const uint32_t k_mn = umma_desc_lo(smem_u32(k_smem), kSub), q_mn = umma_desc_lo(smem_u32(q_smem), kSub);
+      const uint32_t do_mn = umma_desc_lo(smem_u32(do_smem), kSub), ds_mn = umma_desc_lo(smem_u32(ds_smem), kT * 128);
 
-    // D[kv, q] = A[kv, :] . B[q, :]   (both K-major, contraction over the head dim)
-    auto mma_kmajor = [&](uint32_t d_col, uint32_t a_lo, uint32_t b_lo) {
+      // D[kv, q] = A[kv, :] . B[q, :]   (both K-major, contraction over the head dim)
+      auto mma_kmajor = [&](uint32_t d_col, uint32_t a_lo, uint32_t b_lo) {
 #pragma unroll
-      for (int kk = 0; kk < D / 16; ++kk) {
-        const uint32_t off = (kk >> 2) * kSubLo + (kk & 3) * 2;
-        umma_ss(tmem_base + d_col, umma_desc(a_lo + off), umma_desc(b_lo + off), idesc_s, kk > 0 ? 1u : 0u);
-      }
-    };
-    // D[kv, d] (+)= A^T-in-TMEM[kv, q] . B[q, d]   (contraction over the 128 query rows; B MN-major)
-    // the 16-bit A operand sits in columns [0,32) (queries 0-63, written by WG0) and [64,96) (queries 64-127, WG1)
-    auto mma_from_tmem = [&](uint32_t d_col, uint32_t a_col, uint32_t b_lo, bool acc) {
+        for (int kk = 0; kk < D / 16; ++kk) {
+          const uint32_t off = (kk >> 2) * kSubLo + (kk & 3) * 2;
+          umma_ss(tmem_base + d_col, umma_desc(a_lo + off), umma_desc(b_lo + off), idesc_s, kk > 0 ? 1u : 0u);
+        }
+      };
+      // D[kv, d] (+)= A^T-in-TMEM[kv, q] . B[q, d]   (contraction over the 128 query rows; B MN-major)
+      // the 16-bit A operand sits in columns [0,32) (queries 0-63, written by WG0) and [64,96) (queries 64-127, WG1)
+      auto mma_from_tmem = [&](uint32_t d_col, uint32_t a_col, uint32_t b_lo, bool acc) {
 #pragma unroll
-      for (int kk = 0; kk < kT / 16; ++kk) {
-        const uint32_t a = tmem_base + a_col + (kk < 4 ? kk * 8 : 64 + (kk - 4) * 8);
-        umma_ts(tmem_base + d_col, a, umma_desc(b_lo + kk * 128), idesc_acc, (acc || kk > 0) ? 1u : 0u);
-      }
-    };
-    // same product restricted to the first (part 0) or second (part 1) 32 queries of each warpgroup's 64
-    auto mma_from_tmem_part = [&](uint32_t d_col, uint32_t a_col, uint32_t b_lo, bool acc, int part) {
+        for (int kk = 0; kk < kT / 16; ++kk) {
+          const uint32_t a = tmem_base + a_col + (kk < 4 ? kk * 8 : 64 + (kk - 4) * 8);
+          umma_ts(tmem_base + d_col, a, umma_desc(b_lo + kk * 128), idesc_acc, (acc || kk > 0) ? 1u : 0u);
+        }
+      };
+      // same product restricted to the first (part 0) or second (part 1) 32 queries of each warpgroup's 64
+      auto mma_from_tmem_part = [&](uint32_t d_col, uint32_t a_col, uint32_t b_lo, bool acc, int part) {
 #pragma unroll
-      for (int x = 0; x < 4; ++x) {
-        const int kk = (x >> 1) * 4 + part * 2 + (x & 1);  // part 0: 0,1,4,5   part 1: 2,3,6,7
-        const uint32_t a = tmem_base + a_col + (kk < 4 ? kk * 8 : 64 + (kk - 4) * 8);
-        umma_ts(tmem_base + d_col, a, umma_desc(b_lo + kk * 128), idesc_acc, (acc || x > 0) ? 1u : 0u);
-      }
-    };
-    // dQ[q, d] = dS[q, kv] . K[kv, d]   (contraction over the 128 kv rows; both operands MN-major)
-    auto mma_dq = [&]() {
+        for (int x = 0; x < 4; ++x) {
+          const int kk = (x >> 1) * 4 + part * 2 + (x & 1);  // part 0: 0,1,4,5   part 1: 2,3,6,7
+          const uint32_t a = tmem_base + a_col + (kk < 4 ? kk * 8 : 64 + (kk - 4) * 8);
+          umma_ts(tmem_base + d_col, a, umma_desc(b_lo + kk * 128), idesc_acc, (acc || x > 0) ? 1u : 0u);
+        }
+      };
+      // dQ[q, d] = dS[q, kv] . K[kv, d]   (contraction over the 128 kv rows; both operands MN-major)
+      auto mma_dq = [&]() {
 #pragma unroll
-      for (int kk = 0; kk < kT / 16; ++kk)
-        umma_ss(tmem_base + kColDPT, umma_desc(ds_mn + kk * 128), umma_desc(k_mn + kk * 128), idesc_dq,
-                kk > 0 ? 1u : 0u);
-    };
+        for (int kk = 0; kk < kT / 16; ++kk)
+          umma_ss(tmem_base + kColDPT, umma_desc(ds_mn + kk * 128), umma_desc(k_mn + kk * 128), idesc_dq,
+                  kk > 0 ? 1u : 0u);
+      };
 
-    int gt0 = 0, act = 0;  // query tiles / active items before the current item
-    for (int round = 0; round < n_rounds; ++round) {
-      const BwdItem item = bwd_item(p, round);
-      const int n_iter = item.n_iter;
-      if (n_iter == 0) continue;
-      mbar_wait(&bars[kBarKV], act & 1);
-      if (warp == 13 && lane == 0) FA_TRACE(17, gt0);
+      mbar_wait(&bars[kBarKV], 0);
       if (warp == 13) {
         // ---------------- stream X: S^T and dV ----------------
-        // Q(it) is read by S^T(it) [X] and dK(it) [Y]: each stream releases it once its own reader is issued.
-        // S^T(0) of an item follows dV(last) of the previous item in this in-order stream, which consumed the P^T
-        // that lived in the same columns.
-        mbar_wait(&bars[kBarQFull0 + (gt0 & 1)], (gt0 >> 1) & 1);
+        mbar_wait(&bars[kBarQFull0], 0);
         tc_fence_after();
+        // Q(it) is read by S^T(it) [X] and dK(it) [Y]: each stream releases it once its own reader is issued.
         if (elect_one()) {
-          mma_kmajor(kColST, k_km, q_km + (gt0 & 1) * kTileLo);
+          mma_kmajor(kColST, k_km, q_km);
           tc_commit(&bars[kBarSFull]);
-          tc_commit(&bars[kBarQEmpty0 + (gt0 & 1)]);
+          tc_commit(&bars[kBarQEmpty0]);
         }
         __syncwarp();
         for (int it = 0; it < n_iter; ++it) {
-          const int gt = gt0 + it;
-          const uint32_t st = gt & 1;
-          mbar_wait(&bars[kBarDOFull0 + st], (gt >> 1) & 1);
-          mbar_wait(&bars[kBarPReady], gt & 1);
+          const uint32_t st = it & 1;
+          mbar_wait(&bars[kBarDOFull0 + st], (it >> 1) & 1);
+          mbar_wait(&bars[kBarPReady], it & 1);
           // dP^T(it) heads the loop that sets the iteration period (dP -> dS -> dK.dQ -> drain -> dP(next)): let stream Y
           // put it into the tensor pipe first; dV(it) and S^T(it+1) have a whole iteration of slack
-          mbar_wait(&bars[kBarDPIssued], gt & 1);
-          if (it == 0 && act > 0) mbar_wait(&bars[kBarAccFree], (act - 1) & 1);  // previous item's dV has been read out
+          mbar_wait(&bars[kBarDPIssued], it & 1);
           tc_fence_after();
-          if (lane == 0) FA_TRACE(0, gt);
+          if (lane == 0) FA_TRACE(0, it);
           if (elect_one()) {
             mma_from_tmem(kColDV, kColST, do_mn + st * kTileLo, it > 0);  // dV(it) += P^T dO
             tc_commit(&bars[kBarDOEmpty0 + st]);
           }
           __syncwarp();
           if (it + 1 < n_iter) {
-            mbar_wait(&bars[kBarQFull0 + (st ^ 1)], ((gt + 1) >> 1) & 1);
+            mbar_wait(&bars[kBarQFull0 + (st ^ 1)], ((it + 1) >> 1) & 1);
             tc_fence_after();
-            if (lane == 0) FA_TRACE(1, gt);
+            if (lane == 0) FA_TRACE(1, it);
             if (elect_one()) {
               // S^T(it+1): P^T(it) in the same columns has been consumed by dV(it) (in-order within this stream)
               mma_kmajor(kColST, k_km, q_km + (st ^ 1) * kTileLo);
@@ -375,12 +383,11 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
       } else {
         // ---------------- stream Y: dP^T, dK, dQ ----------------
         for (int it = 0; it < n_iter; ++it) {
-          const int gt = gt0 + it;
-          const uint32_t st = gt & 1;
-          mbar_wait(&bars[kBarDOFull0 + st], (gt >> 1) & 1);
-          if (gt > 0) mbar_wait(&bars[kBarDQDrained], (gt - 1) & 1);  // dP^T reuses the columns of the previous dQ
+          const uint32_t st = it & 1;
+          mbar_wait(&bars[kBarDOFull0 + st], (it >> 1) & 1);
+          if (it > 0) mbar_wait(&bars[kBarDQDrained], (it - 1) & 1);  // dP^T reuses the dQ(it-1) columns
           tc_fence_after();
-          if (lane == 0) FA_TRACE(2, gt);
+          if (lane == 0) FA_TRACE(2, it);
           if (elect_one()) {
             mma_kmajor(kColDPT, v_km, do_km + st * kTileLo);  // dP^T(it) = V dO^T
             tc_commit(&bars[kBarDPFull]);
@@ -388,17 +395,16 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
             mbar_arrive(&bars[kBarDPIssued]);
           }
           __syncwarp();
-          mbar_wait(&bars[kBarQFull0 + st], (gt >> 1) & 1);
+          mbar_wait(&bars[kBarQFull0 + st], (it >> 1) & 1);
           // dK(it) += dS^T Q reads the packed dS^T straight from the DPT columns (A operand in TMEM): its first half
           // starts as soon as the first 32 queries of each warpgroup are stored ...
-          mbar_wait(&bars[kBarDSHalf], gt & 1);
-          if (it == 0 && act > 0) mbar_wait(&bars[kBarAccFree], (act - 1) & 1);  // previous item's dK has been read out
+          mbar_wait(&bars[kBarDSHalf], it & 1);
           tc_fence_after();
           if (elect_one()) mma_from_tmem_part(kColDK, kColDPT, q_mn + st * kTileLo, it > 0, 0);
           __syncwarp();
-          mbar_wait(&bars[kBarDSReady], gt & 1);
+          mbar_wait(&bars[kBarDSReady], it & 1);
           tc_fence_after();
-          if (lane == 0) FA_TRACE(3, gt);
+          if (lane == 0) FA_TRACE(3, it);
           if (elect_one()) {
             mma_from_tmem_part(kColDK, kColDPT, q_mn + st * kTileLo, true, 1);  // ... the second half once all are
             tc_commit(&bars[kBarQEmpty0 + st]);
@@ -408,10 +414,9 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
           __syncwarp();
         }
       }
-      tc_commit_elect(&bars[kBarDKVDone]);  // both streams: every product of this item has finished (count 2)
-      gt0 += n_iter;
-      ++act;
+      tc_commit_elect(&bars[kBarDKVDone]);
     }
+    __syncwarp();
   } else if (warp >= 8 && warp < 12) {
     // ===================================== dQ drain warpgroup =====================================
     const int row = threadIdx.x - 256;  // query row inside the tile == TMEM lane
@@ -422,80 +427,74 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
     // for more than a full iteration, so the slow L2 reduce never sits on anyone's critical path.
     // `dq_drained` is signalled as soon as the LAST TMEM read has landed; `stage_free` (which gates the producer's
     // next load into this dO stage) once the last TMA read of the staging buffers has finished.
-    int gt0 = 0;
-    for (int round = 0; round < n_rounds; ++round) {
-      const BwdItem item = bwd_item(p, round);
-      for (int it = 0; it < item.n_iter; ++it) {
-        const int gt = gt0 + it;
-        const int i = item.i_min + it, st = gt & 1, bh = item.bh;
-        uint8_t* dq_smem = Cfg::kStageInDO ? do_smem + st * Cfg::kTileBytes : smem + Cfg::kOffStage;
-        mbar_wait(&bars[kBarDQFull], gt & 1);
-        if constexpr (Cfg::kStageInDO)
-          mbar_wait(&bars[kBarDOEmpty0 + st], (gt >> 1) & 1);  // dV(it) (other MMA stream) has finished reading dO(it)
-        tc_fence_after();
-        if (row == 0) FA_TRACE(8, gt);
-        float v[64];
-        // 32 fp32 columns of this row -> one 128-byte swizzled row of staging buffer `cb`
-        auto stage_chunk = [&](int cb, int off) {
-          uint8_t* rowp = dq_smem + cb * Cfg::kDqStageBytes + row * 128;
+    for (int it = 0, i = first_tile; it < n_iter; ++it, i = next_tile(i)) {
+      const int st = it & 1;
+      uint8_t* dq_smem = Cfg::kStageInDO ? do_smem + st * Cfg::kTileBytes : smem + Cfg::kOffStage;
+      mbar_wait(&bars[kBarDQFull], it & 1);
+      if constexpr (Cfg::kStageInDO)
+        mbar_wait(&bars[kBarDOEmpty0 + st], (it >> 1) & 1);  // dV(it) (other MMA stream) has finished reading dO(it)
+      tc_fence_after();
+      if (row == 0) FA_TRACE(8, it);
+      float v[64];
+      // 32 fp32 columns of this row -> one 128-byte swizzled row of staging buffer `cb`
+      auto stage_chunk = [&](int cb, int off) {
+        uint8_t* rowp = dq_smem + cb * Cfg::kDqStageBytes + row * 128;
 #pragma unroll
-          for (int c = 0; c < 8; ++c)
-            *reinterpret_cast<float4*>(rowp + ((c ^ (row & 7)) << 4)) =
-                make_float4(v[off + 4 * c], v[off + 4 * c + 1], v[off + 4 * c + 2], v[off + 4 * c + 3]);
-        };
-        auto reduce_chunk = [&](int cb, int col) {
-          if (col < p.d) tma_reduce_add_3d(&tm_dq, dq_smem + cb * Cfg::kDqStageBytes, col, i * kT, bh);
-          tma_store_commit();
-        };
-        tmem_ld32(tmem_base + lane_sel + kColDPT, reinterpret_cast<uint32_t*>(v));
-        tmem_ld32(tmem_base + lane_sel + kColDPT + 32, reinterpret_cast<uint32_t*>(v) + 32);
+        for (int c = 0; c < 8; ++c)
+          *reinterpret_cast<float4*>(rowp + ((c ^ (row & 7)) << 4)) =
+              make_float4(v[off + 4 * c], v[off + 4 * c + 1], v[off + 4 * c + 2], v[off + 4 * c + 3]);
+      };
+      auto reduce_chunk = [&](int cb, int col) {
+        if (col < p.d) tma_reduce_add_3d(&tm_dq, dq_smem + cb * Cfg::kDqStageBytes, col, i * kT, bh);
+        tma_store_commit();
+      };
+      tmem_ld32(tmem_base + lane_sel + kColDPT, reinterpret_cast<uint32_t*>(v));
+      tmem_ld32(tmem_base + lane_sel + kColDPT + 32, reinterpret_cast<uint32_t*>(v) + 32);
+      tc_wait_ld();
+      stage_chunk(0, 0);
+      stage_chunk(1, 32);
+      if (D == 128) {  // second 64 columns straight away: TMEM goes back before any TMA bookkeeping
+        tmem_ld32(tmem_base + lane_sel + kColDPT + 64, reinterpret_cast<uint32_t*>(v));
+        tmem_ld32(tmem_base + lane_sel + kColDPT + 96, reinterpret_cast<uint32_t*>(v) + 32);
         tc_wait_ld();
-        stage_chunk(0, 0);
-        stage_chunk(1, 32);
-        if (D == 128) {  // second 64 columns straight away: TMEM goes back before any TMA bookkeeping
-          tmem_ld32(tmem_base + lane_sel + kColDPT + 64, reinterpret_cast<uint32_t*>(v));
-          tmem_ld32(tmem_base + lane_sel + kColDPT + 96, reinterpret_cast<uint32_t*>(v) + 32);
-          tc_wait_ld();
+      }
+      tc_fence_before();
+      mbar_arrive(&bars[kBarDQDrained]);
+      if (row == 0) FA_TRACE(9, it);
+      fence_proxy_async_smem();
+      named_bar_sync(3, 128);
+      if (row == 0) {
+        reduce_chunk(0, 0);
+        reduce_chunk(1, 32);
+      }
+      if (D == 128) {
+        // columns 64-127 follow through the same two buffers, each as soon as its previous reduce has been read, so
+        // the reduce engine (about 40 B/ns per SM, measured) never waits for the staging stores of a whole half
+        if (row == 0) {
+          tma_store_wait_read<1>();
+          FA_TRACE(10, it);
         }
-        tc_fence_before();
-        mbar_arrive(&bars[kBarDQDrained]);
-        if (row == 0) FA_TRACE(9, gt);
+        named_bar_sync(3, 128);
+        stage_chunk(0, 0);
         fence_proxy_async_smem();
         named_bar_sync(3, 128);
         if (row == 0) {
-          reduce_chunk(0, 0);
-          reduce_chunk(1, 32);
+          reduce_chunk(0, 64);
+          tma_store_wait_read<1>();
         }
-        if (D == 128) {
-          // columns 64-127 follow through the same two buffers, each as soon as its previous reduce has been read, so
-          // the reduce engine (about 40 B/ns per SM, measured) never waits for the staging stores of a whole half
-          if (row == 0) {
-            tma_store_wait_read<1>();
-            FA_TRACE(10, gt);
-          }
-          named_bar_sync(3, 128);
-          stage_chunk(0, 0);
-          fence_proxy_async_smem();
-          named_bar_sync(3, 128);
-          if (row == 0) {
-            reduce_chunk(0, 64);
-            tma_store_wait_read<1>();
-          }
-          named_bar_sync(3, 128);
-          stage_chunk(1, 32);
-          fence_proxy_async_smem();
-          named_bar_sync(3, 128);
-          if (row == 0) reduce_chunk(1, 96);
-        }
-        if (row == 0) {
-          FA_TRACE(14, gt);
-          tma_store_wait_read<0>();
-          mbar_arrive(&bars[kBarStageFree0 + st]);
-          FA_TRACE(11, gt);
-        }
-        if constexpr (!Cfg::kStageInDO) named_bar_sync(3, 128);  // dedicated staging is reused by the very next tile
+        named_bar_sync(3, 128);
+        stage_chunk(1, 32);
+        fence_proxy_async_smem();
+        named_bar_sync(3, 128);
+        if (row == 0) reduce_chunk(1, 96);
       }
-      gt0 += item.n_iter;
+      if (row == 0) {
+        FA_TRACE(14, it);
+        tma_store_wait_read<0>();
+        mbar_arrive(&bars[kBarStageFree0 + st]);
+        FA_TRACE(11, it);
+      }
+      if constexpr (!Cfg::kStageInDO) named_bar_sync(3, 128);  // dedicated staging is reused by the very next tile
     }
     if (row == 0) tma_store_wait_exit();  // staging read; the reduce itself completes by grid end
   } else if (warp < 8) {
@@ -507,197 +506,222 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
     const uint32_t t_st = tmem_base + lane_sel + kColST + col_base;
     const uint32_t t_dpt = tmem_base + lane_sel + kColDPT + col_base;
     uint8_t* ds_row = ds_smem + wg * (kT * 128) + r * 128;
-    // dK / dV write-out staging: this warpgroup's own 16 KiB half of the dS^T tile (nobody else touches it, and its
-    // next use is this warpgroup's own dS write of the next item), so K, V, Q and dO stay with the producer
-    uint8_t* out_stage = ds_smem + wg * (kT * 128);
+
+    const bool dropout = kExt && p.drop_threshold != 0;
+    for (int it = 0, i = first_tile; it < n_iter; ++it, i = next_tile(i)) {
+      const int st = it & 1;
+      const float* ls = stats_smem + st * 256 + col_base;  // -lse * log2e for this WG's 64 query columns
+      const float* dl = ls + 128;                          // -delta
+      // key (j*128 + r) is visible to query (i*128 + c) iff c >= c_min
+      // ... and keys past n_kv (zero-filled by TMA) are never visible
+      const bool kv_tail = (j * kT + kT > p.n_kv);
+      int c_min = p.causal ? r + (j - i) * kT - p.diag : 0;
+      if (j * kT + r >= p.n_kv) c_min = 1 << 30;
+      const bool need_mask = kv_tail || (p.causal && (kT - 1 + (j - i) * kT - p.diag > 0));
+
+      mbar_wait(&bars[kBarQFull0 + st], (it >> 1) & 1);  // row statistics ride on the Q barrier
+      mbar_wait(&bars[kBarSFull], it & 1);
+      tc_fence_after();
+      if (threadIdx.x == 0) FA_TRACE(4, it);
+      if (threadIdx.x == 0 && it == 0) FA_LIFE(3, clock64());  // first scores have arrived
+#ifdef FA_BWD_TRACE
+      if (threadIdx.x == 0 && fa_bwd_lin_block() == fa_bwd_trace_block && it < FA_BWD_TRACE_ITERS) {
+        long long gt;  // wall-clock ns next to the cycle stamp: calibrates the SM clock under load
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        fa_bwd_trace_buf[15 * FA_BWD_TRACE_ITERS + it] = gt;
+      }
+#endif
+      float pr[64];
+      uint32_t keep[2] = {0xffffffffu, 0xffffffffu};  // kExt + dropout: keep bit of each of this thread's 64 queries
+      const float2 c2 = make_float2(p.scale_log2, p.scale_log2);
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        float s[32];
+        tmem_ld32(t_st + c * 32, reinterpret_cast<uint32_t*>(s));
+        tc_wait_ld();
+        uint32_t pk[16];
+#pragma unroll
+        for (int x4 = 0; x4 < 8; ++x4) {
+          const float4 l4 = *reinterpret_cast<const float4*>(ls + c * 32 + x4 * 4);  // -lse * log2e
+          const float2 t0 = ffma2(make_float2(s[x4 * 4], s[x4 * 4 + 1]), c2, make_float2(l4.x, l4.y));
+          const float2 t1 = ffma2(make_float2(s[x4 * 4 + 2], s[x4 * 4 + 3]), c2, make_float2(l4.z, l4.w));
+          float pv[4] = {ex2(t0.x), ex2(t0.y), ex2(t1.x), ex2(t1.y)};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int x = x4 * 4 + e;
+            if (need_mask) pv[e] = (col_base + c * 32 + x >= c_min) ? pv[e] : 0.f;
+            pr[c * 32 + x] = pv[e];
+          }
+          if constexpr (kExt) {
+            if (dropout) {  // one Philox call covers these 4 queries (words) x 4 keys (bytes): ours is byte kv & 3
+              const uint32_t kg = static_cast<uint32_t>(p.kv_col0 + j * kT + r);
+              const uint32_t qg = static_cast<uint32_t>(p.q_row0 + i * kT + col_base + c * 32 + x4 * 4);
+              const Philox4 rr = philox4x32_7(qg >> 2, kg >> 2, static_cast<uint32_t>(bh), p.rng_offset, p.seed_lo,
+                                              p.seed_hi);
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                if (((rr.w[e] >> ((kg & 3) * 8)) & 0xFFu) < p.drop_threshold) keep[c] &= ~(1u << (x4 * 4 + e));
+            }
+          }
+        }
+        // P^T as the dV operand carries the dropout (P o keep / (1 - p)); pr keeps the un-dropped P for dS
+#pragma unroll
+        for (int x = 0; x < 16; ++x) {
+          float a = pr[c * 32 + 2 * x], b = pr[c * 32 + 2 * x + 1];
+          if constexpr (kExt) {
+            if (dropout) {
+              a = ((keep[c] >> (2 * x)) & 1u) ? a * p.drop_scale : 0.f;
+              b = ((keep[c] >> (2 * x + 1)) & 1u) ? b * p.drop_scale : 0.f;
+            }
+          }
+          pk[x] = pack2<kBF16>(a, b);
+        }
+        tmem_st16(t_st + c * 16, pk);
+      }
+      tc_wait_st();
+      tc_fence_before();
+      mbar_arrive(&bars[kBarPReady]);
+      if (threadIdx.x == 0) FA_TRACE(5, it);
+      mbar_wait(&bars[kBarDPFull], it & 1);
+      tc_fence_after();
+      if (threadIdx.x == 0) FA_TRACE(6, it);
+      {
+        // dS^T = P o (dP^T - delta) in four 16-column steps; the TMEM load of step c+1 is in flight while step c is
+        // computed, converted and written twice: packed over the consumed dP^T columns in TMEM (A operand of dK) and to
+        // the swizzled shared-memory tile (A operand of dQ, which needs the un-transposed view)
+        float dp[2][16];
+        tmem_ld16(t_dpt, reinterpret_cast<uint32_t*>(dp[0]));
+        tc_wait_ld();
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          if (c + 1 < 4) tmem_ld16(t_dpt + (c + 1) * 16, reinterpret_cast<uint32_t*>(dp[(c + 1) & 1]));
+          float* dpc = dp[c & 1];
+          if constexpr (kExt) {
+            if (dropout) {  // dP = (dO V^T) o keep / (1 - p)
+#pragma unroll
+              for (int x = 0; x < 16; ++x)
+                dpc[x] = ((keep[c >> 1] >> ((c & 1) * 16 + x)) & 1u) ? dpc[x] * p.drop_scale : 0.f;
+            }
+          }
+          uint32_t pk[8];
+#pragma unroll
+          for (int x4 = 0; x4 < 4; ++x4) {
+            const float4 d4 = *reinterpret_cast<const float4*>(dl + c * 16 + x4 * 4);  // -delta
+            const int x = x4 * 4;
+            const float2 a = fmul2(make_float2(pr[c * 16 + x], pr[c * 16 + x + 1]),
+                                   fadd2(make_float2(dpc[x], dpc[x + 1]), make_float2(d4.x, d4.y)));
+            const float2 b = fmul2(make_float2(pr[c * 16 + x + 2], pr[c * 16 + x + 3]),
+                                   fadd2(make_float2(dpc[x + 2], dpc[x + 3]), make_float2(d4.z, d4.w)));
+            pk[x >> 1] = pack2<kBF16>(a.x, a.y);
+            pk[(x >> 1) + 1] = pack2<kBF16>(b.x, b.y);
+          }
+#pragma unroll
+          for (int ch = 0; ch < 2; ++ch) {
+            const int chunk = c * 2 + ch;
+            *reinterpret_cast<uint4*>(ds_row + ((chunk ^ (r & 7)) << 4)) =
+                make_uint4(pk[4 * ch], pk[4 * ch + 1], pk[4 * ch + 2], pk[4 * ch + 3]);
+          }
+          if (c + 1 < 4) tc_wait_ld();
+          tmem_st8(t_dpt + c * 8, pk);  // packed dS^T over the dP^T columns this thread has already consumed
+          if (c == 1) {  // first 32 queries of this warpgroup are in TMEM: dK can start on them
+            tc_wait_st();
+            tc_fence_before();
+            mbar_arrive(&bars[kBarDSHalf]);
+          }
+        }
+      }
+      tc_wait_st();
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(&bars[kBarDSReady]);
+      if (threadIdx.x == 0) FA_TRACE(7, it);
+    }
+
+    // ------------------------------- epilogue: WG0 stores dV, WG1 stores dK * scale -------------------------------
+    if (threadIdx.x == 0) FA_LIFE(4, clock64());  // last dS handed over
+    if (n_iter > 0) {
+      mbar_wait(&bars[kBarDKVDone], 0);
+      tc_fence_after();
+      if (threadIdx.x == 0) FA_LIFE(5, clock64());  // last dK/dV products finished
+    } else {
+      mbar_wait(&bars[kBarKV], 0);  // staging reuses the K/V tiles: their loads must have landed
+    }
+    uint8_t* stage_tile = wg == 0 ? v_smem : k_smem;
     const uint32_t t_acc = tmem_base + lane_sel + (wg == 0 ? kColDV : kColDK);
     const float mul = wg == 0 ? 1.f : p.scale;
-    const CUtensorMap* tm_out = wg == 0 ? &tm_dv : &tm_dk;
-
-    int gt0 = 0, act = 0;
-    for (int round = 0; round < n_rounds; ++round) {
-      const BwdItem item = bwd_item(p, round);
-      if (!item.valid) continue;
-      const int n_iter = item.n_iter, j = item.j, bh = item.bh;
-      for (int it = 0; it < n_iter; ++it) {
-        const int gt = gt0 + it;
-        const int i = item.i_min + it, st = gt & 1;
-        const float* ls = stats_smem + st * 256 + col_base;  // -lse * log2e for this WG's 64 query columns
-        const float* dl = ls + 128;                          // -delta
-        // key (j*128 + r) is visible to query (i*128 + c) iff c >= c_min
-        // ... and keys past n_kv (zero-filled by TMA) are never visible
-        const bool kv_tail = (j * kT + kT > p.n_kv);
-        int c_min = p.causal ? r + (j - i) * kT - p.diag : 0;
-        if (j * kT + r >= p.n_kv) c_min = 1 << 30;
-        const bool need_mask = kv_tail || (p.causal && (kT - 1 + (j - i) * kT - p.diag > 0));
-
-        mbar_wait(&bars[kBarQFull0 + st], (gt >> 1) & 1);  // row statistics ride on the Q barrier
-        mbar_wait(&bars[kBarSFull], gt & 1);
-        tc_fence_after();
-        if (threadIdx.x == 0) FA_TRACE(4, gt);
-        float pr[64];
-        const float2 c2 = make_float2(p.scale_log2, p.scale_log2);
+    const CUtensorMap* tm = wg == 0 ? &tm_dv : &tm_dk;
+    if (!p.accum_kv) {
+      // 16-bit results: the whole tile goes through the (dead) V / K buffer and out with one TMA store per 64 columns
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          float s[32];
-          tmem_ld32(t_st + c * 32, reinterpret_cast<uint32_t*>(s));
-          tc_wait_ld();
-          uint32_t pk[16];
-#pragma unroll
-          for (int x4 = 0; x4 < 8; ++x4) {
-            const float4 l4 = *reinterpret_cast<const float4*>(ls + c * 32 + x4 * 4);  // -lse * log2e
-            const float2 t0 = ffma2(make_float2(s[x4 * 4], s[x4 * 4 + 1]), c2, make_float2(l4.x, l4.y));
-            const float2 t1 = ffma2(make_float2(s[x4 * 4 + 2], s[x4 * 4 + 3]), c2, make_float2(l4.z, l4.w));
-            float pv[4] = {ex2(t0.x), ex2(t0.y), ex2(t1.x), ex2(t1.y)};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int x = x4 * 4 + e;
-              if (need_mask) pv[e] = (col_base + c * 32 + x >= c_min) ? pv[e] : 0.f;
-              pr[c * 32 + x] = pv[e];
-            }
-          }
-#pragma unroll
-          for (int x = 0; x < 16; ++x) pk[x] = pack2<kBF16>(pr[c * 32 + 2 * x], pr[c * 32 + 2 * x + 1]);
-          tmem_st16(t_st + c * 16, pk);
-        }
-        tc_wait_st();
-        tc_fence_before();
-        mbar_arrive(&bars[kBarPReady]);
-        if (threadIdx.x == 0) FA_TRACE(5, gt);
-
-        mbar_wait(&bars[kBarDPFull], gt & 1);
-        tc_fence_after();
-        if (threadIdx.x == 0) FA_TRACE(6, gt);
-        {
-          // dS^T = P o (dP^T - delta) in four 16-column steps; the TMEM load of step c+1 is in flight while step c is
-          // computed, converted and written twice: packed over the consumed dP^T columns in TMEM (A operand of dK) and to
-          // the swizzled shared-memory tile (A operand of dQ, which needs the un-transposed view)
-          float dp[2][16];
-          tmem_ld16(t_dpt, reinterpret_cast<uint32_t*>(dp[0]));
-          tc_wait_ld();
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            if (c + 1 < 4) tmem_ld16(t_dpt + (c + 1) * 16, reinterpret_cast<uint32_t*>(dp[(c + 1) & 1]));
-            const float* dpc = dp[c & 1];
-            uint32_t pk[8];
-#pragma unroll
-            for (int x4 = 0; x4 < 4; ++x4) {
-              const float4 d4 = *reinterpret_cast<const float4*>(dl + c * 16 + x4 * 4);  // -delta
-              const int x = x4 * 4;
-              const float2 a = fmul2(make_float2(pr[c * 16 + x], pr[c * 16 + x + 1]),
-                                     fadd2(make_float2(dpc[x], dpc[x + 1]), make_float2(d4.x, d4.y)));
-              const float2 b = fmul2(make_float2(pr[c * 16 + x + 2], pr[c * 16 + x + 3]),
-                                     fadd2(make_float2(dpc[x + 2], dpc[x + 3]), make_float2(d4.z, d4.w)));
-              pk[x >> 1] = pack2<kBF16>(a.x, a.y);
-              pk[(x >> 1) + 1] = pack2<kBF16>(b.x, b.y);
-            }
-#pragma unroll
-            for (int ch = 0; ch < 2; ++ch) {
-              const int chunk = c * 2 + ch;
-              *reinterpret_cast<uint4*>(ds_row + ((chunk ^ (r & 7)) << 4)) =
-                  make_uint4(pk[4 * ch], pk[4 * ch + 1], pk[4 * ch + 2], pk[4 * ch + 3]);
-            }
-            if (c + 1 < 4) tc_wait_ld();
-            tmem_st8(t_dpt + c * 8, pk);  // packed dS^T over the dP^T columns this thread has already consumed
-            if (c == 1) {  // first 32 queries of this warpgroup are in TMEM: dK can start on them
-              tc_wait_st();
-              tc_fence_before();
-              mbar_arrive(&bars[kBarDSHalf]);
-            }
-          }
-        }
-        tc_wait_st();
-        fence_proxy_async_smem();
-        tc_fence_before();
-        mbar_arrive(&bars[kBarDSReady]);
-        if (threadIdx.x == 0) FA_TRACE(7, gt);
-      }
-
-      // ------------------------------- item epilogue: WG0 writes dV, WG1 writes dK * scale -------------------------------
-      // Runs while the producer and the MMA warps are already on the next item: K/V/Q/dO are not touched, TMEM is
-      // handed back (acc_free) right after the last accumulator read.
-      if (n_iter > 0) {
-        mbar_wait(&bars[kBarDKVDone], act & 1);  // every product of the item is complete (also the last dQ: the dS^T
-        tc_fence_after();                         // tile in shared memory is dead)
-        if (threadIdx.x == 0) FA_TRACE(15, gt0 + n_iter - 1);
-      }
-      if (!p.accum_kv) {
-        // 16-bit results, 64 columns (one 16 KiB swizzled sub-tile) per round
-#pragma unroll
-        for (int round64 = 0; round64 < kChunks; ++round64) {
-#pragma unroll
-          for (int q4 = 0; q4 < 2; ++q4) {
-            float a[32];
-            if (n_iter > 0) {
-              tmem_ld32(t_acc + round64 * 64 + q4 * 32, reinterpret_cast<uint32_t*>(a));
-              tc_wait_ld();
-            } else {
-#pragma unroll
-              for (int x = 0; x < 32; ++x) a[x] = 0.f;
-            }
-            if (n_iter > 0 && round64 == kChunks - 1 && q4 == 1) {  // last accumulator read: the next item may overwrite
-              tc_fence_before();
-              mbar_arrive(&bars[kBarAccFree]);
-            }
-            uint32_t pk[16];
-#pragma unroll
-            for (int x = 0; x < 16; ++x) pk[x] = pack2<kBF16>(a[2 * x] * mul, a[2 * x + 1] * mul);
-            uint8_t* sub = out_stage + r * 128;
-#pragma unroll
-            for (int ch = 0; ch < 4; ++ch) {
-              const int chunk = q4 * 4 + ch;
-              *reinterpret_cast<uint4*>(sub + ((chunk ^ (r & 7)) << 4)) =
-                  make_uint4(pk[4 * ch], pk[4 * ch + 1], pk[4 * ch + 2], pk[4 * ch + 3]);
-            }
-          }
-          fence_proxy_async_smem();
-          named_bar_sync(1 + wg, 128);
-          if (r == 0) {
-            tma_store_3d(tm_out, out_stage, round64 * 64, j * kT, bh);
-            tma_store_commit();
-            tma_store_wait_read<0>();
-          }
-          named_bar_sync(1 + wg, 128);  // the staging half is free again (next round / next item's dS^T)
-        }
-      } else if (n_iter > 0) {
-        // fp32 accumulators that travel with the K/V block (ring attention): the partial is reduce-added in fp32, 32
-        // columns (one 128-byte swizzled row per kv row, 16 KiB) per round.  tm_dv / tm_dk describe the fp32
-        // accumulators here.
-#pragma unroll
-        for (int q4 = 0; q4 < D / 32; ++q4) {
-          float a[32];
+      for (int q4 = 0; q4 < D / 32; ++q4) {
+        float a[32];
+        if (n_iter > 0) {
           tmem_ld32(t_acc + q4 * 32, reinterpret_cast<uint32_t*>(a));
           tc_wait_ld();
-          if (q4 == D / 32 - 1) {
-            tc_fence_before();
-            mbar_arrive(&bars[kBarAccFree]);
-          }
-          uint8_t* rowp = out_stage + r * 128;
+        } else {
+#pragma unroll
+          for (int x = 0; x < 32; ++x) a[x] = 0.f;
+        }
+        uint32_t pk[16];
+#pragma unroll
+        for (int x = 0; x < 16; ++x) pk[x] = pack2<kBF16>(a[2 * x] * mul, a[2 * x + 1] * mul);
+        uint8_t* sub = stage_tile + (q4 >> 1) * kSub + r * 128;
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+          const int chunk = (q4 & 1) * 4 + ch;
+          *reinterpret_cast<uint4*>(sub + ((chunk ^ (r & 7)) << 4)) =
+              make_uint4(pk[4 * ch], pk[4 * ch + 1], pk[4 * ch + 2], pk[4 * ch + 3]);
+        }
+      }
+      fence_proxy_async_smem();
+      named_bar_sync(1 + wg, 128);
+      if (r == 0) {
+        for (int ch = 0; ch < kChunks; ++ch) tma_store_3d(tm, stage_tile + ch * kSub, ch * 64, j * kT, bh);
+        tma_store_commit();
+        tma_store_wait_exit();  // K/V staging has been read; the stores complete by grid end
+      }
+    } else if (n_iter > 0) {
+      // fp32 accumulators that travel with the K/V block (ring attention): the partial is reduce-added in fp32, 32
+      // columns (one 128-byte swizzled row per kv row, 16 KiB) at a time, D/64 such chunks per round through the
+      // same V / K buffer.  tm_dv / tm_dk describe the fp32 accumulators here.
+      constexpr int kPerRound = D / 64;
+#pragma unroll
+      for (int round = 0; round < 2; ++round) {
+#pragma unroll
+        for (int u = 0; u < kPerRound; ++u) {
+          float a[32];
+          tmem_ld32(t_acc + (round * kPerRound + u) * 32, reinterpret_cast<uint32_t*>(a));
+          tc_wait_ld();
+          uint8_t* rowp = stage_tile + u * Cfg::kDqStageBytes + r * 128;
 #pragma unroll
           for (int c = 0; c < 8; ++c)
             *reinterpret_cast<float4*>(rowp + ((c ^ (r & 7)) << 4)) =
                 make_float4(a[4 * c] * mul, a[4 * c + 1] * mul, a[4 * c + 2] * mul, a[4 * c + 3] * mul);
-          fence_proxy_async_smem();
-          named_bar_sync(1 + wg, 128);
-          if (r == 0) {
-            if (q4 * 32 < p.d) tma_reduce_add_3d(tm_out, out_stage, q4 * 32, j * kT, bh);
-            tma_store_commit();
-            tma_store_wait_read<0>();
-          }
-          named_bar_sync(1 + wg, 128);
         }
+        fence_proxy_async_smem();
+        named_bar_sync(1 + wg, 128);
+        if (r == 0) {
+          for (int u = 0; u < kPerRound; ++u) {
+            const int col = (round * kPerRound + u) * 32;
+            if (col < p.d) tma_reduce_add_3d(tm, stage_tile + u * Cfg::kDqStageBytes, col, j * kT, bh);
+          }
+          tma_store_commit();
+          tma_store_wait_read<0>();
+        }
+        named_bar_sync(1 + wg, 128);  // the buffer is free for the next round / safe to leave
       }
-      if (threadIdx.x == 0 && n_iter > 0) FA_TRACE(16, gt0 + n_iter - 1);
-      gt0 += n_iter;
-      if (n_iter > 0) ++act;
     }
-    if (r == 0) tma_store_wait_exit();  // the stores themselves complete by grid end
   }
 
   tc_fence_before();
   __syncthreads();
   if (warp == 13) tmem_dealloc(tmem_base, 512);
-  FA_SPAN(1);
+#ifdef FA_BWD_TRACE
+  if (threadIdx.x == 0) {
+    FA_LIFE(6, clock64());
+    FA_LIFE(7, fa_bwd_globaltimer());
+  }
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -760,11 +784,12 @@ fa_bwd_prepare_kernel(const uint16_t* __restrict__ o, const uint16_t* __restrict
   }
 }
 
-template <int D, bool kBF16>
-static int launch_bwd(const Geometry& g, const void* q, const void* k, const void* v, const void* d_o,
-                      const float* rowstats, float* dq_accum, void* dk, void* dv, bool accum_kv,
+template <int D, bool kBF16, bool kExt>
+static int launch_bwd(const Geometry& g, const ExtArgs& ext, const void* q, const void* k, const void* v,
+                      const void* d_o, const float* rowstats, float* dq_accum, void* dk, void* dv, bool accum_kv,
                       long long acc_bh_stride, cudaStream_t stream) {
   using Cfg = BwdCfg<D>;
+  constexpr int kSmem = kExt ? Cfg::kSmemBytesExt : Cfg::kSmemBytes;
   const int elem = kBF16 ? kElemBF16 : kElemF16;
   CUtensorMap tm_q, tm_k, tm_v, tm_do, tm_dq, tm_dk, tm_dv;
   int rc;
@@ -795,24 +820,34 @@ static int launch_bwd(const Geometry& g, const void* q, const void* k, const voi
   p.nqt = static_cast<int>((g.n_q + kT - 1) / kT);
   p.nkt = static_cast<int>((g.n_kv + kT - 1) / kT);
   p.group_log2 = sched_group_log2(g.causal != 0, p.nkt, g.bh);
-  const long long n_groups = (g.bh + (1ll << p.group_log2) - 1) >> p.group_log2;
-  p.n_items = (n_groups * p.nkt) << p.group_log2;
+  while (((g.bh + (1ll << p.group_log2) - 1) >> p.group_log2) > 65535) ++p.group_log2;  // grid.z limit
   p.scale = g.scale;
   p.scale_log2 = g.scale * 1.4426950408889634f;
 
-  auto kern = fa_bwd_kernel<D, kBF16>;
+  p.block_mask = ext.block_mask;
+  p.mask_bh_stride = ext.mask_bh_stride;
+  p.seed_lo = ext.seed_lo;
+  p.seed_hi = ext.seed_hi;
+  p.rng_offset = ext.rng_offset;
+  p.drop_threshold = ext.drop_threshold;
+  p.drop_scale = ext.drop_scale;
+  p.q_row0 = ext.q_row0;
+  p.kv_col0 = ext.kv_col0;
+  auto kern = fa_bwd_kernel<D, kBF16, kExt>;
   static bool attr_set[64];  // per device (function attributes are per context); benign race: idempotent
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes) != cudaSuccess)
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem) != cudaSuccess)
       return FA_SM100_ELAUNCH;
     if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
-  const long long ctas = persistent_ctas(p.n_items);
-  if (ctas <= 0) return FA_SM100_EDEVICE;
-  const dim3 grid(static_cast<unsigned>(ctas), 1, 1);
-  kern<<<grid, kBwdThreads, Cfg::kSmemBytes, stream>>>(tm_q, tm_k, tm_v, tm_do, tm_dq, tm_dk, tm_dv, p);
+  const long long rank_lo = p.nkt < (1 << kRankBitsY) ? p.nkt : (1 << kRankBitsY);
+  const long long rank_hi = (p.nkt + (1 << kRankBitsY) - 1) >> kRankBitsY;
+  const long long gx = rank_hi << p.group_log2, gz = (g.bh + (1ll << p.group_log2) - 1) >> p.group_log2;
+  if (gx > 0x7fffffffll || gz > 65535) return FA_SM100_EINVAL_SHAPE;
+  const dim3 grid(static_cast<unsigned>(gx), static_cast<unsigned>(rank_lo), static_cast<unsigned>(gz));
+  kern<<<grid, kBwdThreads, kSmem, stream>>>(tm_q, tm_k, tm_v, tm_do, tm_dq, tm_dk, tm_dv, p);
   return launch_status();
 }
 
@@ -854,12 +889,14 @@ extern "C" int fa_sm100_bwd_prepare(const fa_sm100_shape* s, const void* o, cons
 }
 
 namespace fa {
-static int bwd_dispatch(const fa_sm100_shape* s, const void* q, const void* k, const void* v, const void* d_o,
-                        const float* rowstats, float* dq_accum, void* dk, void* dv, bool accum_kv,
+static int bwd_dispatch(const fa_sm100_shape* s, const fa_sm100_ext* ext, const void* q, const void* k, const void* v,
+                        const void* d_o, const float* rowstats, float* dq_accum, void* dk, void* dv, bool accum_kv,
                         long long acc_bh_stride, void* stream) {
   Geometry g;
   int rc = check_shape(s, &g);
   if (rc) return rc;
+  ExtArgs ea;
+  if ((rc = check_ext(ext, s, kMaxMaskTiles, &ea))) return rc;
   if (!aligned16(q) || !aligned16(k) || !aligned16(v) || !aligned16(d_o) || !aligned16(rowstats) ||
       !aligned16(dq_accum) || !aligned16(dk) || !aligned16(dv))
     return FA_SM100_EINVAL_PTR;
@@ -870,40 +907,49 @@ static int bwd_dispatch(const fa_sm100_shape* s, const void* q, const void* k, c
   if ((rc = check_device())) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const bool bf = g.dtype == FA_SM100_DTYPE_BF16;
-  if (g.dp == 128) {
-    return bf ? launch_bwd<128, true>(g, q, k, v, d_o, rowstats, dq_accum, dk, dv, accum_kv, acc_bh_stride, st)
-              : launch_bwd<128, false>(g, q, k, v, d_o, rowstats, dq_accum, dk, dv, accum_kv, acc_bh_stride, st);
+#define FA_BWD_GO(DD, BF, EXT) \
+  launch_bwd<DD, BF, EXT>(g, ea, q, k, v, d_o, rowstats, dq_accum, dk, dv, accum_kv, acc_bh_stride, st)
+  if (ea.block_mask == nullptr && ea.drop_threshold == 0) {  // the dense kernel
+    if (g.dp == 128) return bf ? FA_BWD_GO(128, true, false) : FA_BWD_GO(128, false, false);
+    return bf ? FA_BWD_GO(64, true, false) : FA_BWD_GO(64, false, false);
   }
-  return bf ? launch_bwd<64, true>(g, q, k, v, d_o, rowstats, dq_accum, dk, dv, accum_kv, acc_bh_stride, st)
-            : launch_bwd<64, false>(g, q, k, v, d_o, rowstats, dq_accum, dk, dv, accum_kv, acc_bh_stride, st);
+  if (g.dp == 128) return bf ? FA_BWD_GO(128, true, true) : FA_BWD_GO(128, false, true);
+  return bf ? FA_BWD_GO(64, true, true) : FA_BWD_GO(64, false, true);
+#undef FA_BWD_GO
 }
 }  // namespace fa
 
 extern "C" int fa_sm100_bwd(const fa_sm100_shape* s, const void* q, const void* k, const void* v, const void* d_o,
                             const float* rowstats, float* dq_accum, void* dk, void* dv, void* stream) {
-  return fa::bwd_dispatch(s, q, k, v, d_o, rowstats, dq_accum, dk, dv, false, 0, stream);
+  return fa::bwd_dispatch(s, nullptr, q, k, v, d_o, rowstats, dq_accum, dk, dv, false, 0, stream);
+}
+
+extern "C" int fa_sm100_bwd_ex(const fa_sm100_shape* s, const fa_sm100_ext* ext, const void* q, const void* k,
+                               const void* v, const void* d_o, const float* rowstats, float* dq_accum, void* dk,
+                               void* dv, void* stream) {
+  return fa::bwd_dispatch(s, ext, q, k, v, d_o, rowstats, dq_accum, dk, dv, false, 0, stream);
 }
 
 extern "C" int fa_sm100_bwd_accum(const fa_sm100_shape* s, const void* q, const void* k, const void* v,
                                   const void* d_o, const float* rowstats, float* dq_accum, float* dk_accum,
                                   float* dv_accum, int64_t acc_bh_stride, void* stream) {
-  return fa::bwd_dispatch(s, q, k, v, d_o, rowstats, dq_accum, dk_accum, dv_accum, true, acc_bh_stride, stream);
+  return fa::bwd_dispatch(s, nullptr, q, k, v, d_o, rowstats, dq_accum, dk_accum, dv_accum, true, acc_bh_stride, stream);
 }
 
 #ifdef FA_BWD_TRACE
 // debug build only: select the CTA to trace / copy its timeline (events x FA_BWD_TRACE_ITERS clock64 values) to the host
+extern "C" int fa_sm100_debug_bwd_life(long long* host_dst, int n_ctas) {
+  if (!host_dst || n_ctas <= 0 || n_ctas > FA_BWD_LIFE_MAX_CTAS) return -1;
+  return cudaMemcpyFromSymbol(host_dst, fa_bwd_life_buf, sizeof(long long) * 8 * n_ctas) == cudaSuccess ? n_ctas : -1;
+}
 extern "C" int fa_sm100_debug_bwd_trace(int set_block, long long* host_dst, int max_values) {
   if (set_block >= 0) {
-    static long long zero[FA_BWD_TRACE_EVENTS * FA_BWD_TRACE_ITERS] = {};
+    long long zero[FA_BWD_TRACE_EVENTS * FA_BWD_TRACE_ITERS] = {};
     cudaMemcpyToSymbol(fa_bwd_trace_buf, zero, sizeof(zero));
     return cudaMemcpyToSymbol(fa_bwd_trace_block, &set_block, sizeof(int)) == cudaSuccess ? 0 : -1;
   }
   const int n = FA_BWD_TRACE_EVENTS * FA_BWD_TRACE_ITERS;
   if (!host_dst || max_values < n) return -1;
   return cudaMemcpyFromSymbol(host_dst, fa_bwd_trace_buf, n * sizeof(long long)) == cudaSuccess ? n : -1;
-}
-extern "C" int fa_sm100_debug_bwd_spans(long long* host_dst, int n_ctas) {
-  if (!host_dst || n_ctas <= 0 || n_ctas > 256) return -1;
-  return cudaMemcpyFromSymbol(host_dst, fa_bwd_span_buf, sizeof(long long) * 2 * n_ctas) == cudaSuccess ? n_ctas : -1;
 }
 #endif

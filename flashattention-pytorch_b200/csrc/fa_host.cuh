@@ -111,34 +111,39 @@ inline int sched_group_log2(bool skewed, long long n_ranks, long long n_slices) 
   while ((2ll << lg) <= g && (2ll << lg) <= n_slices) ++lg;  // largest power of two <= min(g, n_slices)
   return lg;
 }
-// Persistent grids: one CTA per SM, minus `sm_margin` SMs left free for concurrently running communication kernels
-// (NCCL send/recv in the ring-attention schedule cannot make progress under 148 resident one-CTA-per-SM kernels).
-// The margin is process-wide state set through fa_sm100_set_sm_margin() or the FA_SM100_SM_MARGIN environment variable.
-inline int& sm_margin_ref() {
-  static int margin = [] {
-    const char* e = std::getenv("FA_SM100_SM_MARGIN");
-    const int v = e ? std::atoi(e) : 0;
-    return v > 0 ? v : 0;
-  }();
-  return margin;
-}
-inline long long persistent_ctas(long long n_items) {
-  static const bool one_item_per_cta = [] {  // FA_SM100_PERSISTENT=0: measurement knob, one CTA per work item
-    const char* e = std::getenv("FA_SM100_PERSISTENT");
-    return e != nullptr && e[0] == '0';
-  }();
-  if (one_item_per_cta) return n_items;
-  static int sms[64];  // per device; benign race: idempotent writes
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess) return -1;
-  int n = (dev >= 0 && dev < 64) ? sms[dev] : 0;
-  if (n == 0) {
-    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return -1;
-    if (dev >= 0 && dev < 64) sms[dev] = n;
+// Validated form of fa_sm100_ext.
+struct ExtArgs {
+  const uint8_t* block_mask = nullptr;
+  long long mask_bh_stride = 0;
+  int mask_cols = 0;
+  uint32_t seed_lo = 0, seed_hi = 0, rng_offset = 0, drop_threshold = 0;
+  float drop_scale = 1.f;
+  long long q_row0 = 0, kv_col0 = 0;
+};
+inline int check_ext(const fa_sm100_ext* e, const fa_sm100_shape* s, int max_tiles, ExtArgs* out) {
+  *out = ExtArgs();
+  out->q_row0 = s->q_row0;
+  out->kv_col0 = s->kv_col0;
+  out->mask_cols = static_cast<int>((s->n_kv + 127) / 128);
+  if (e == nullptr) return FA_SM100_OK;
+  if (!(e->dropout_p >= 0.f) || !(e->dropout_p < 1.f)) return FA_SM100_EINVAL_EXT;
+  const uint32_t thr = static_cast<uint32_t>(e->dropout_p * 256.f);  // floor: p quantised to 1/256
+  if (thr > 0) {
+    if ((s->q_row0 % 4) || (s->kv_col0 % 4) || s->q_row0 < 0 || s->kv_col0 < 0) return FA_SM100_EINVAL_EXT;
+    out->drop_threshold = thr;
+    out->drop_scale = 256.f / static_cast<float>(256u - thr);
+    out->seed_lo = static_cast<uint32_t>(e->seed);
+    out->seed_hi = static_cast<uint32_t>(e->seed >> 32);
+    out->rng_offset = static_cast<uint32_t>(e->offset);
   }
-  long long ctas = n - sm_margin_ref();
-  if (ctas < 1) ctas = 1;
-  return n_items < ctas ? n_items : ctas;
+  if (e->block_mask != nullptr) {
+    const long long rows = (s->n_q + 127) / 128, cols = (s->n_kv + 127) / 128;
+    if (rows > max_tiles || cols > max_tiles) return FA_SM100_EINVAL_EXT;
+    if (e->mask_bh_stride != 0 && e->mask_bh_stride < rows * cols) return FA_SM100_EINVAL_EXT;
+    out->block_mask = e->block_mask;
+    out->mask_bh_stride = e->mask_bh_stride;
+  }
+  return FA_SM100_OK;
 }
 inline int launch_status() { return cudaGetLastError() == cudaSuccess ? FA_SM100_OK : FA_SM100_ELAUNCH; }
 

@@ -443,6 +443,30 @@ __device__ __forceinline__ float2 ex2_poly2(float2 t) {
   return p;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Dropout random bits: Philox4x32-7 (counter-based, so the forward and the backward regenerate the same bits from the
+// element's coordinates with no stored mask).  One call covers a 4 x 4 block of (query, key) elements:
+//   counter = (query >> 2, key >> 2, slice, offset),  key = (seed_lo, seed_hi);
+//   output word (query & 3), byte (key & 3) is the element's random byte; it is KEPT iff byte >= threshold.
+// Both kernels therefore need 16 calls per 64 elements whichever of the two indices a thread walks.
+// ------------------------------------------------------------------------------------------------
+struct Philox4 { uint32_t w[4]; };
+__host__ __device__ __forceinline__ Philox4 philox4x32_7(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                         uint32_t k0, uint32_t k1) {
+  constexpr uint32_t kM0 = 0xD2511F53u, kM1 = 0xCD9E8D57u, kW0 = 0x9E3779B9u, kW1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 7; ++r) {
+    const uint64_t p0 = static_cast<uint64_t>(kM0) * c0, p1 = static_cast<uint64_t>(kM1) * c2;
+    const uint32_t n0 = static_cast<uint32_t>(p1 >> 32) ^ c1 ^ k0, n1 = static_cast<uint32_t>(p1);
+    const uint32_t n2 = static_cast<uint32_t>(p0 >> 32) ^ c3 ^ k1, n3 = static_cast<uint32_t>(p0);
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += kW0; k1 += kW1;
+  }
+  Philox4 out;
+  out.w[0] = c0; out.w[1] = c1; out.w[2] = c2; out.w[3] = c3;
+  return out;
+}
+
 // pack two fp32 -> one 32-bit word of two 16-bit floats; `lo` lands in the low half (= even element index)
 template <bool kBF16>
 __device__ __forceinline__ uint32_t pack2(float lo, float hi) {

@@ -53,14 +53,29 @@ class _Shape(ctypes.Structure):
     ]
 
 
+class _Ext(ctypes.Structure):
+    """Mirror of ``fa_sm100_ext`` (include/fa_sm100.h): block-sparse tile mask + dropout."""
+
+    _fields_ = [
+        ("block_mask", ctypes.c_void_p),
+        ("mask_bh_stride", ctypes.c_int64),
+        ("dropout_p", ctypes.c_float),
+        ("seed", ctypes.c_uint64),
+        ("offset", ctypes.c_uint64),
+    ]
+
+
 # every symbol include/fa_sm100.h declares: name -> (restype, argtypes)
 _P = ctypes.c_void_p
 _SP = ctypes.POINTER(_Shape)
+_EP = ctypes.POINTER(_Ext)
 ABI = {
     "fa_sm100_version": (ctypes.c_int, []),
     "fa_sm100_strerror": (ctypes.c_char_p, [ctypes.c_int]),
     "fa_sm100_dq_accum_bytes": (ctypes.c_size_t, [_SP]),
     "fa_sm100_fwd": (ctypes.c_int, [_SP, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "fa_sm100_fwd_ex": (ctypes.c_int, [_SP, _EP, _P, _P, _P, _P, _P, _P]),
+    "fa_sm100_bwd_ex": (ctypes.c_int, [_SP, _EP, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "fa_sm100_rowstats_bytes": (ctypes.c_size_t, [_SP]),
     "fa_sm100_bwd_prepare": (ctypes.c_int, [_SP, _P, _P, _P, _P, _P, _P]),
     "fa_sm100_bwd": (ctypes.c_int, [_SP, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
@@ -279,6 +294,74 @@ def bwd_raw(q, k, v, o, do, lse, causal, softmax_scale, *, q_row0=0, kv_col0=0, 
                                 _stream_ptr(q)), "fa_sm100_bwd")
     if ring:
         return None, dk, dv
+    return dq_finish_raw(dq_accum, q.dtype, softmax_scale), dk, dv
+
+
+BLOCK = 128  # tile edge of the block-sparse mask (the reference's default block_size)
+
+
+def _make_ext(block_mask, bh, n_q, n_kv, dropout_p, seed, offset):
+    """(ctypes struct, tensors to keep alive).  ``block_mask``: (ceil(n_q/128), ceil(n_kv/128)) shared by all slices or
+    (bh, ...) per slice, any integer / bool dtype, nonzero = compute the tile."""
+    keep = None
+    ptr, stride = None, 0
+    if block_mask is not None:
+        rows, cols = (n_q + BLOCK - 1) // BLOCK, (n_kv + BLOCK - 1) // BLOCK
+        if block_mask.dim() == 2:
+            want = (rows, cols)
+        elif block_mask.dim() == 3:
+            want, stride = (bh, rows, cols), rows * cols
+        else:
+            raise RuntimeError("block_sparse_mask must be (q_blocks, k_blocks) or (batch*heads, q_blocks, k_blocks)")
+        if tuple(block_mask.shape) != want:
+            raise RuntimeError(f"block_sparse_mask has shape {tuple(block_mask.shape)}, expected {want} "
+                               f"(block size {BLOCK})")
+        keep = (block_mask != 0).to(torch.uint8).contiguous()
+        ptr = keep.data_ptr()
+    if not (0.0 <= float(dropout_p) < 1.0):
+        raise ValueError("dropout_p must be in [0, 1)")
+    return _Ext(ptr, stride, float(dropout_p), int(seed) & (2 ** 64 - 1), int(offset) & (2 ** 64 - 1)), keep
+
+
+def fwd_ex_raw(q, k, v, causal, softmax_scale, *, block_mask=None, dropout_p=0.0, seed=0, offset=0, q_row0=0,
+               kv_col0=0):
+    """Forward with a 128 x 128 block-sparse mask and / or dropout (C ABI ``fa_sm100_fwd_ex``)."""
+    lib = load_library()
+    bh, n_q, d = q.shape
+    n_kv = k.shape[1]
+    out = _empty_like_strided(q)
+    lse = torch.empty((bh, n_q), device=q.device, dtype=torch.float32)
+    ext, keep = _make_ext(block_mask, bh, n_q, n_kv, dropout_p, seed, offset)
+    shape = make_shape(bh, n_q, n_kv, d, _dtype_code(q), causal, softmax_scale, q_row0, kv_col0,
+                       _same_stride(q, out), _same_stride(k, v), _slice_stride(lse))
+    with torch.cuda.device(q.device):
+        _check(lib.fa_sm100_fwd_ex(ctypes.byref(shape), ctypes.byref(ext), q.data_ptr(), k.data_ptr(), v.data_ptr(),
+                                   out.data_ptr(), lse.data_ptr(), _stream_ptr(q)), "fa_sm100_fwd_ex")
+    if keep is not None:
+        keep.record_stream(torch.cuda.current_stream(q.device))
+    return out, lse
+
+
+def bwd_ex_raw(q, k, v, o, do, lse, causal, softmax_scale, *, block_mask=None, dropout_p=0.0, seed=0, offset=0,
+               q_row0=0, kv_col0=0):
+    """Backward matching ``fwd_ex_raw`` (same mask, dropout_p, seed, offset).  Returns (dq, dk, dv)."""
+    lib = load_library()
+    bh, n_q, d = q.shape
+    n_kv = k.shape[1]
+    if bh > 1 and _slice_stride(q) != n_q * d:
+        q, do, o = q.contiguous(), do.contiguous(), o.contiguous()
+    dq_accum = torch.empty(q.shape, device=q.device, dtype=torch.float32)
+    rowstats = bwd_prepare_raw(o, do, lse, zero=dq_accum)
+    dk, dv = _empty_like_strided(k), _empty_like_strided(k)
+    ext, keep = _make_ext(block_mask, bh, n_q, n_kv, dropout_p, seed, offset)
+    shape = make_shape(bh, n_q, n_kv, d, _dtype_code(q), causal, softmax_scale, q_row0, kv_col0,
+                       _same_stride(q, do, dq_accum), _same_stride(k, v, dk, dv), 0)
+    with torch.cuda.device(q.device):
+        _check(lib.fa_sm100_bwd_ex(ctypes.byref(shape), ctypes.byref(ext), q.data_ptr(), k.data_ptr(), v.data_ptr(),
+                                   do.data_ptr(), rowstats.data_ptr(), dq_accum.data_ptr(), dk.data_ptr(),
+                                   dv.data_ptr(), _stream_ptr(q)), "fa_sm100_bwd_ex")
+    if keep is not None:
+        keep.record_stream(torch.cuda.current_stream(q.device))
     return dq_finish_raw(dq_accum, q.dtype, softmax_scale), dk, dv
 
 

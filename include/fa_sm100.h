@@ -40,6 +40,7 @@ extern "C" {
 #define FA_SM100_EDRIVER (-6)        /* could not resolve / call cuTensorMapEncodeTiled */
 #define FA_SM100_ELAUNCH (-7)        /* kernel launch failed (cudaGetLastError) */
 #define FA_SM100_EDEVICE (-8)        /* current device is not compute capability 10.x */
+#define FA_SM100_EINVAL_EXT (-9)     /* bad fa_sm100_ext: dropout_p outside [0,1), offsets not multiples of 4, too many tiles */
 
 /* Problem geometry shared by all entry points. */
 typedef struct fa_sm100_shape {
@@ -56,6 +57,27 @@ typedef struct fa_sm100_shape {
   int64_t kv_bh_stride;  /* elements between slices of k / v / dk / dv                (0 => n_kv * d)  */
   int64_t lse_bh_stride; /* elements between slices of lse / delta                    (0 => n_q)       */
 } fa_sm100_shape;
+
+/*
+ * Optional extras of the *_ex entry points (the block-sparse mask and dropout of the
+ * reference's stand-alone module, src/fa3/torch/flashattention_pytorch.py:80-87,94-174):
+ *   block_mask : uint8 DEVICE array, (ceil(n_q/128) x ceil(n_kv/128)) row-major per slice, or one shared by all slices
+ *                (mask_bh_stride = 0).  Tile (i, j) is computed iff block_mask[i][j] != 0; a skipped tile contributes
+ *                nothing (as if its scores were -inf).  NULL = dense.  Block size is fixed at 128 (the reference's
+ *                default, :19); the causal mask, if any, applies on top.
+ *   dropout    : probabilities are dropped after the softmax: O = (P o keep / (1 - p)) V; lse is unaffected.
+ *                keep bits come from Philox4x32-7 keyed by (seed, offset) and the element's GLOBAL (slice, query,
+ *                key) coordinates, so forward and backward regenerate the same bits and a sharded run equals the
+ *                unsharded one.  p is quantised to multiples of 1/256: an element is dropped iff its random byte <
+ *                floor(p * 256).  q_row0 and kv_col0 must be multiples of 4 when dropout is on.
+ */
+typedef struct fa_sm100_ext {
+  const uint8_t* block_mask;
+  int64_t mask_bh_stride; /* elements between the masks of consecutive slices; 0 = one mask shared by all slices */
+  float dropout_p;        /* [0, 1); 0 = no dropout */
+  uint64_t seed;
+  uint64_t offset;
+} fa_sm100_ext;
 
 int fa_sm100_version(void);
 const char* fa_sm100_strerror(int code);
@@ -79,6 +101,10 @@ size_t fa_sm100_rowstats_bytes(const fa_sm100_shape* s);
 int fa_sm100_fwd(const fa_sm100_shape* s, const void* q, const void* k, const void* v, void* o, float* lse,
                  const void* o_prev, const float* lse_prev, void* stream);
 
+/* Forward with the extras above (ext == NULL behaves like fa_sm100_fwd without a previous partial). */
+int fa_sm100_fwd_ex(const fa_sm100_shape* s, const fa_sm100_ext* ext, const void* q, const void* k, const void* v,
+                    void* o, float* lse, void* stream);
+
 /*
  * Backward pre-pass (reference csrc/fa1/fa1_bwd.cu:57): delta[r] = sum_c dO[r,c] * O[r,c], packed together with
  * lse[r] * log2(e) into `rowstats`, both NEGATED: for slice b and 128-row tile t, floats [(b*T + t)*256, +128) hold
@@ -98,6 +124,11 @@ int fa_sm100_bwd_prepare(const fa_sm100_shape* s, const void* o, const void* d_o
  */
 int fa_sm100_bwd(const fa_sm100_shape* s, const void* q, const void* k, const void* v, const void* d_o,
                  const float* rowstats, float* dq_accum, void* dk, void* dv, void* stream);
+
+/* Backward main pass with the extras above: the same mask / (p, seed, offset) the forward ran with.  With dropout,
+ * dV = (P o keep / (1-p))^T dO,  dP = (dO V^T) o keep / (1-p),  dS = P o (dP - delta)  (delta from the dropped O). */
+int fa_sm100_bwd_ex(const fa_sm100_shape* s, const fa_sm100_ext* ext, const void* q, const void* k, const void* v,
+                    const void* d_o, const float* rowstats, float* dq_accum, void* dk, void* dv, void* stream);
 
 /*
  * Ring-attention form of the main pass: instead of writing dk / dv, the fp32 partials (dK already scaled) are

@@ -231,3 +231,93 @@ def relative_error(actual, expected, tile_rows=128):
     worst = float((num[ok] / den[ok]).max()) if ok.any() else 0.0
     return {"rel_fro": total, "worst_tile_rel_fro": worst}
 
+
+# ----------------------------------------------------------------------------------------------------------------------
+# block-sparse mask + dropout
+# ----------------------------------------------------------------------------------------------------------------------
+_PHILOX_M0, _PHILOX_M1, _PHILOX_W0, _PHILOX_W1 = 0xD2511F53, 0xCD9E8D57, 0x9E3779B9, 0xBB67AE85
+_U32 = 0xFFFFFFFF
+
+
+def philox4x32_7(c0, c1, c2, c3, k0, k1, rounds=7):
+    """Philox4x32 (Salmon et al., "Parallel random numbers: as easy as 1, 2, 3", SC'11) on int64 tensors holding 32-bit
+    values; 7 rounds is what the kernels use for dropout (csrc/ptx.cuh philox4x32_7), ``rounds=10`` reproduces the
+    published known-answer vectors (tests/test_oracle_golden.py).  Returns the four output words."""
+    def mulhilo(a, b):  # 32x32 -> (hi, lo) without overflowing int64: split b into 16-bit halves
+        lo_part = a * (b & 0xFFFF)
+        hi_part = a * (b >> 16)
+        full_lo = (lo_part + ((hi_part & 0xFFFF) << 16))
+        lo = full_lo & _U32
+        hi = ((hi_part >> 16) + (full_lo >> 32)) & _U32
+        return hi, lo
+
+    c0, c1, c2, c3 = (x.clone() & _U32 for x in (c0, c1, c2, c3))
+    for _ in range(rounds):
+        hi0, lo0 = mulhilo(c0, _PHILOX_M0)
+        hi1, lo1 = mulhilo(c2, _PHILOX_M1)
+        c0, c1, c2, c3 = (hi1 ^ c1 ^ k0) & _U32, lo1, (hi0 ^ c3 ^ k1) & _U32, lo0
+        k0, k1 = (k0 + _PHILOX_W0) & _U32, (k1 + _PHILOX_W1) & _U32
+    return c0, c1, c2, c3
+
+
+def dropout_keep_mask(bh, n_q, n_kv, dropout_p, seed, offset=0, q_row0=0, kv_col0=0):
+    """(bh, n_q, n_kv) bool keep mask and the rescale factor, bit-for-bit what the kernels generate: one Philox call
+    per 4 x 4 block of (query, key) elements, counter (query >> 2, key >> 2, slice, offset), key (seed lo, seed hi);
+    the element's byte is word (query & 3), byte (key & 3); it is dropped iff byte < floor(p * 256)."""
+    thr = int(float(dropout_p) * 256.0)
+    if thr == 0:
+        return torch.ones((bh, n_q, n_kv), dtype=torch.bool), 1.0
+    qg = (torch.arange(n_q, dtype=torch.int64) + q_row0)[None, :, None]
+    kg = (torch.arange(n_kv, dtype=torch.int64) + kv_col0)[None, None, :]
+    sl = torch.arange(bh, dtype=torch.int64)[:, None, None]
+    shape = (bh, n_q, n_kv)
+    words = philox4x32_7((qg >> 2).expand(shape), (kg >> 2).expand(shape), sl.expand(shape),
+                         torch.full(shape, int(offset) & _U32, dtype=torch.int64), int(seed) & _U32,
+                         (int(seed) >> 32) & _U32)
+    w = torch.stack(words, dim=-1).gather(-1, (qg & 3).expand(shape)[..., None]).squeeze(-1)
+    byte = (w >> ((kg & 3) * 8).expand(shape)) & 0xFF
+    return byte >= thr, 256.0 / (256.0 - thr)
+
+
+def expand_block_mask(block_mask, n_q, n_kv, block=128):
+    """(…, ceil(n_q/block), ceil(n_kv/block)) tile mask -> (…, n_q, n_kv) element mask (nonzero = visible)."""
+    m = (block_mask != 0)
+    m = m.repeat_interleave(block, dim=-2).repeat_interleave(block, dim=-1)
+    return m[..., :n_q, :n_kv]
+
+
+def dense_ext_backward_fp32(q, k, v, do, causal=False, softmax_scale=None, block_mask=None, dropout_p=0.0, seed=0,
+                            offset=0, q_row0=0, kv_col0=0):
+    """fp32 forward + closed-form gradients of
+        O = dropout(softmax(mask(Q K^T * scale))) V
+    as the dense branch of the reference's stand-alone module computes it (src/fa3/torch/flashattention_pytorch.py:80-87:
+    masked_fill(mask == 0, -inf) -> softmax -> dropout -> @ v), with the block-sparse tile mask (:124) expanded to
+    elements and the kernels' Philox keep mask.  Returns (dq, dk, dv, o, lse); lse ignores dropout."""
+    if softmax_scale is None:
+        softmax_scale = q.shape[-1] ** -0.5
+    qf, kf, vf, dof = (t.float().cpu() for t in (q, k, v, do))
+    bh, n_q, _ = qf.shape
+    n_kv = kf.shape[1]
+    s = torch.matmul(qf, kf.transpose(-2, -1)) * softmax_scale
+    vis = torch.ones((n_q, n_kv), dtype=torch.bool)
+    if causal:
+        vis = visible_mask(n_q, n_kv, q_row0, kv_col0)
+    vis = vis[None].expand(bh, n_q, n_kv)
+    if block_mask is not None:
+        bm = expand_block_mask(block_mask.cpu(), n_q, n_kv)
+        vis = vis & (bm if bm.dim() == 3 else bm[None])
+    s = s.masked_fill(~vis, NEG_INF)
+    lse = torch.logsumexp(s, dim=-1)
+    p = torch.exp(s - torch.where(torch.isinf(lse), torch.zeros_like(lse), lse)[..., None])
+    keep, rescale = dropout_keep_mask(bh, n_q, n_kv, dropout_p, seed, offset, q_row0, kv_col0)
+    z = keep.float() * rescale
+    pd = p * z
+    o = torch.matmul(pd, vf)
+    delta = (dof * o).sum(-1, keepdim=True)
+    dv = torch.matmul(pd.transpose(-2, -1), dof)
+    dp = torch.matmul(dof, vf.transpose(-2, -1)) * z
+    ds = p * (dp - delta)
+    dq = torch.matmul(ds, kf) * softmax_scale
+    dk = torch.matmul(ds.transpose(-2, -1), qf) * softmax_scale
+    return dq, dk, dv, o, lse
+

@@ -80,6 +80,13 @@ def test_argument_validation_happens_before_any_cuda_call():
     s = ext.make_shape(**good)
     assert lib.fa_sm100_fwd(ctypes.byref(s), None, fake, fake, fake, fake, None, None, None) == -4
     assert lib.fa_sm100_fwd(ctypes.byref(s), ctypes.c_void_p(260), fake, fake, fake, fake, None, None, None) == -4
+    # extras: dropout_p outside [0, 1), offsets that are not multiples of 4 with dropout on
+    bad = ext._Ext(None, 0, 1.0, 0, 0)
+    assert lib.fa_sm100_fwd_ex(ctypes.byref(s), ctypes.byref(bad), fake, fake, fake, fake, fake, None) == -9
+    s2 = ext.make_shape(**{**good, "q_row0": 2})
+    drop = ext._Ext(None, 0, 0.5, 1, 0)
+    assert lib.fa_sm100_fwd_ex(ctypes.byref(s2), ctypes.byref(drop), fake, fake, fake, fake, fake, None) == -9
+    assert b"extras" in lib.fa_sm100_strerror(-9)
 
 
 def test_shape_struct_layout_matches_header():
@@ -87,9 +94,14 @@ def test_shape_struct_layout_matches_header():
 
     # 3*8 + 3*4 + 4 + 5*8 = 80 bytes with natural alignment
     assert ctypes.sizeof(ext._Shape) == 80
-    fields = [f[0] for f in ext._Shape._fields_]
-    order = re.findall(r"^\s+(?:int64_t|int32_t|float)\s+(\w+);", HEADER, flags=re.M)
-    assert fields == order
+    def struct_fields(name):
+        body = re.search(r"typedef struct " + name + r" \{(.*?)\} " + name + ";", HEADER, flags=re.S).group(1)
+        return re.findall(r"^\s+(?:const\s+)?(?:u?int64_t|int32_t|float|uint8_t\*)\s+(\w+);", body, flags=re.M)
+
+    assert [f[0] for f in ext._Shape._fields_] == struct_fields("fa_sm100_shape")
+    # fa_sm100_ext: pointer, int64, float (+4 pad), uint64, uint64 = 40 bytes
+    assert [f[0] for f in ext._Ext._fields_] == struct_fields("fa_sm100_ext")
+    assert ctypes.sizeof(ext._Ext) == 40
 
 
 @pytest.mark.parametrize("n", [1, 2, 3])
