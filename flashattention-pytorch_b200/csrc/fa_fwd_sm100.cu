@@ -553,6 +553,372 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
 #endif
 }
 
+// ------------------------------------------------------------------------------------------------
+// Head dim 129..256 (the reference's benchmark sweeps --head-dim 64 128 256,
+// benchmarks/bench_utils.py:256).  The O accumulator alone takes 256 TMEM columns, so the ping-pong pair of query tiles
+// of the main kernel does not fit: here a CTA owns ONE 128-row query tile and streams 64-row K/V tiles (one softmax
+// step each), S double-buffered in two 64-column TMEM buffers so S(t+1) is computed while the warpgroup exponentiates
+// S(t).  TMEM: S0 [0,64)  S1 [64,128)  O [128,384).  SMEM: Q 64 KiB + 4-stage K/V ring of 32 KiB tiles = 192 KiB.
+// Warps 0-3 softmax (thread = query row), warp 4 TMA producer, warp 5 MMA issuer.  Forward only: a backward at this
+// head dim needs dK and dV accumulators of 256 columns each -- all of TMEM -- and is not provided.
+// ------------------------------------------------------------------------------------------------
+constexpr int kFwd256Threads = 192;
+constexpr int kBN256 = 64;
+struct Fwd256Cfg {
+  static constexpr int kD = 256;
+  static constexpr int kStages = 4;
+  static constexpr int kQBytes = 128 * kD * 2;        // 64 KiB: four 64-column sub-tiles of 16 KiB
+  static constexpr int kQSub = 128 * 128;
+  static constexpr int kKVBytes = kBN256 * kD * 2;    // 32 KiB: four 64-column sub-tiles of 8 KiB
+  static constexpr int kKVSub = kBN256 * 128;
+  static constexpr int kSmemBytes = kQBytes + kStages * kKVBytes + 1024 + 256;
+};
+
+template <bool kBF16>
+__global__ void __launch_bounds__(kFwd256Threads, 1)
+fa_fwd256_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
+                 const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_o, const FwdParams p) {
+  using Cfg = Fwd256Cfg;
+  constexpr int D = Cfg::kD, NS = Cfg::kStages, kChunks = D / 64;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* q_smem = smem;
+  uint8_t* kv_smem = smem + Cfg::kQBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(kv_smem + NS * Cfg::kKVBytes);
+  uint64_t* q_full = bars;            // [1]
+  uint64_t* s_full = bars + 1;        // [2]
+  uint64_t* p_ready = bars + 3;       // [2]
+  uint64_t* pv_done = bars + 5;       // [2]  (split by step parity, see the main kernel)
+  uint64_t* kv_full = bars + 7;       // [NS]
+  uint64_t* kv_empty = bars + 7 + NS; // [NS]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7 + 2 * NS);
+
+  const int warp = static_cast<int>(warp_uniform(threadIdx.x >> 5));
+  const int lane = threadIdx.x & 31;
+  // same grid shape as the main kernel (x = slice in group, y = tile rank heaviest first, z = group); here a rank is
+  // one query tile
+  const uint32_t rank = ((blockIdx.x >> p.group_log2) << kRankBitsY) + blockIdx.y;
+  const int bh = static_cast<int>((blockIdx.z << p.group_log2) + (blockIdx.x & ((1u << p.group_log2) - 1u)));
+  if (bh >= p.bh || rank >= static_cast<uint32_t>(p.npairs)) return;
+  const int tile_row0 = (p.npairs - 1 - static_cast<int>(rank)) * kBM;
+  const int nt = fwd_num_steps(tile_row0, p);  // 64-column steps == K/V tiles to stream
+
+  if (warp == 4 && lane == 0) {
+    mbar_init(&q_full[0], 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_ready[i], 128);
+      mbar_init(&pv_done[i], 1);
+    }
+    for (int i = 0; i < NS; ++i) {
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+    }
+    fence_mbar_init();
+    tma_prefetch_desc(&tm_q);
+    tma_prefetch_desc(&tm_k);
+    tma_prefetch_desc(&tm_v);
+    tma_prefetch_desc(&tm_o);
+    mbar_arrive_expect_tx(&q_full[0], Cfg::kQBytes);
+    for (int c = 0; c < kChunks; ++c) tma_load_3d(q_smem + c * Cfg::kQSub, &tm_q, &q_full[0], c * 64, tile_row0, bh);
+    for (int t = 0; t < 2 * nt && t < NS; ++t) {
+      mbar_arrive_expect_tx(&kv_full[t], Cfg::kKVBytes);
+      const CUtensorMap* tm = (t & 1) ? &tm_v : &tm_k;
+      for (int c = 0; c < kChunks; ++c)
+        tma_load_3d(kv_smem + t * Cfg::kKVBytes + c * Cfg::kKVSub, tm, &kv_full[t], c * 64, (t >> 1) * kBN256, bh);
+    }
+  }
+  if (warp == 5) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = warp_uniform(*tmem_slot);
+
+  if (warp == 4) {
+    // ===================================== TMA producer =====================================
+    if (lane == 0) {
+      for (int t = NS; t < 2 * nt; ++t) {
+        const int stage = t % NS;
+        mbar_wait(&kv_empty[stage], ((t / NS) & 1) ^ 1);
+        mbar_arrive_expect_tx(&kv_full[stage], Cfg::kKVBytes);
+        const CUtensorMap* tm = (t & 1) ? &tm_v : &tm_k;
+        for (int c = 0; c < kChunks; ++c)
+          tma_load_3d(kv_smem + stage * Cfg::kKVBytes + c * Cfg::kKVSub, tm, &kv_full[stage], c * 64, (t >> 1) * kBN256,
+                      bh);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 5) {
+    // ===================================== MMA issuer =====================================
+    if (nt > 0) {
+      constexpr uint32_t idesc_s = umma_idesc(kBF16, kBM, kStep, false, false);  // S = Q K^T, N = 64
+      constexpr uint32_t idesc_o = umma_idesc(kBF16, kBM, D, false, true);       // O += P V, N = 256, V MN-major
+      constexpr uint32_t kStageLo = Cfg::kKVBytes >> 4;
+      const uint32_t q_lo = umma_desc_lo(smem_u32(q_smem), 16);
+      const uint32_t k_lo0 = umma_desc_lo(smem_u32(kv_smem), 16);
+      const uint32_t v_lo0 = umma_desc_lo(smem_u32(kv_smem), Cfg::kKVSub);
+      const uint32_t t_o = tmem_base + 128;
+      auto stage_of = [&](uint32_t slot) { return slot & (NS - 1); };
+      auto phase_of = [&](uint32_t slot) { return (slot / NS) & 1u; };
+      auto issue_s = [&](int step, uint32_t stage) {  // S(step) into buffer step & 1
+        const uint32_t b_lo = k_lo0 + stage * kStageLo;
+        const uint32_t d_tmem = tmem_base + (step & 1) * kStep;
+#pragma unroll
+        for (int kk = 0; kk < D / 16; ++kk)
+          umma_ss(d_tmem, umma_desc(q_lo + (kk >> 2) * (Cfg::kQSub >> 4) + (kk & 3) * 2),
+                  umma_desc(b_lo + (kk >> 2) * (Cfg::kKVSub >> 4) + (kk & 3) * 2), idesc_s, kk > 0 ? 1u : 0u);
+      };
+      auto issue_pv = [&](int step, uint32_t stage, bool acc) {
+        const uint32_t b_lo = v_lo0 + stage * kStageLo;
+        const uint32_t a_tmem = tmem_base + (step & 1) * kStep;
+#pragma unroll
+        for (int kk = 0; kk < kStep / 16; ++kk)
+          umma_ts(t_o, a_tmem + kk * 8, umma_desc(b_lo + kk * 128), idesc_o, (acc || kk > 0) ? 1u : 0u);
+      };
+      mbar_wait(&q_full[0], 0);
+      for (int s0 = 0; s0 < 2 && s0 < nt; ++s0) {  // S(0), S(1): K tiles in ring slots 0 and 2
+        const uint32_t sk = 2 * s0;
+        mbar_wait(&kv_full[stage_of(sk)], phase_of(sk));
+        tc_fence_after();
+        if (elect_one()) {
+          issue_s(s0, stage_of(sk));
+          tc_commit(&s_full[s0]);
+          tc_commit(&kv_empty[stage_of(sk)]);
+        }
+        __syncwarp();
+      }
+      for (int t = 0; t < nt; ++t) {
+        const uint32_t sv = 2 * t + 1;
+        const int s2 = t + 2;
+        const uint32_t sk = 2 * s2;
+        mbar_wait(&kv_full[stage_of(sv)], phase_of(sv));
+        if (s2 < nt) mbar_wait(&kv_full[stage_of(sk)], phase_of(sk));
+        mbar_wait(&p_ready[t & 1], (t >> 1) & 1);
+        tc_fence_after();
+        if (elect_one()) {
+          issue_pv(t, stage_of(sv), t > 0);
+          tc_commit(&pv_done[t & 1]);
+          tc_commit(&kv_empty[stage_of(sv)]);
+          if (s2 < nt) {
+            issue_s(s2, stage_of(sk));
+            tc_commit(&s_full[s2 & 1]);
+            tc_commit(&kv_empty[stage_of(sk)]);
+          }
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ===================================== softmax warpgroup =====================================
+    const int row = threadIdx.x & 127;
+    const int row_l = tile_row0 + row;
+    const uint32_t lane_sel = static_cast<uint32_t>((warp & 3) * 32) << 16;
+    const uint32_t t_s = tmem_base + lane_sel;
+    const uint32_t t_o = tmem_base + lane_sel + 128;
+    const float c = p.scale_log2;
+    int vis = p.n_kv - 1;
+    if (p.causal) {
+      const long long cv = static_cast<long long>(row_l) + p.diag;
+      vis = cv < vis ? static_cast<int>(cv < -1 ? -1 : cv) : vis;
+    }
+    float m_ref = -INFINITY, l_sum = 0.f;
+    for (int j = 0; j < nt; ++j) {
+      const int buf = j & 1;
+      const uint32_t t_sb = t_s + buf * kStep;
+      mbar_wait(&s_full[buf], (j >> 1) & 1);
+      tc_fence_after();
+      float s[kStep];
+      tmem_ld32(t_sb, reinterpret_cast<uint32_t*>(s));
+      tmem_ld32(t_sb + 32, reinterpret_cast<uint32_t*>(s) + 32);
+      tc_wait_ld();
+      const int lim = vis - j * kStep;
+      if (lim < kStep - 1) {
+#pragma unroll
+        for (int x = 0; x < kStep; ++x) s[x] = (x > lim) ? -INFINITY : s[x];
+      }
+      float mx0 = s[0], mx1 = s[1], mx2 = s[2], mx3 = s[3];
+#pragma unroll
+      for (int x = 4; x < kStep; x += 4) {
+        mx0 = fmaxf(mx0, s[x]);
+        mx1 = fmaxf(mx1, s[x + 1]);
+        mx2 = fmaxf(mx2, s[x + 2]);
+        mx3 = fmaxf(mx3, s[x + 3]);
+      }
+      const float m_new = fmaxf(m_ref, fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)));
+      bool rescale = false;
+      float alpha = 1.f;
+      if (j == 0) {
+        m_ref = m_new;
+      } else {
+        const bool need = (m_new - m_ref) * c > kRescaleThreshold;
+        if (__any_sync(0xffffffffu, need)) {
+          const float m_safe = (m_new == -INFINITY) ? 0.f : m_new;
+          alpha = ex2((m_ref - m_safe) * c);
+          l_sum *= alpha;
+          m_ref = m_new;
+          rescale = true;
+        }
+      }
+      const float mc = ((m_ref == -INFINITY) ? 0.f : m_ref) * c;
+      float2 ls_a = make_float2(0.f, 0.f), ls_b = make_float2(0.f, 0.f);
+      const float2 c2 = make_float2(c, c), nmc2 = make_float2(-mc, -mc);
+#pragma unroll
+      for (int q2 = 0; q2 < kStep / 32; ++q2) {
+        uint32_t pk[16];
+#pragma unroll
+        for (int x = 0; x < 16; ++x) {
+          const float2 t = ffma2(make_float2(s[q2 * 32 + 2 * x], s[q2 * 32 + 2 * x + 1]), c2, nmc2);
+          float2 pv;
+          pv.x = ex2(t.x);
+          pv.y = ex2(t.y);
+          if (x & 1) ls_b = fadd2(ls_b, pv); else ls_a = fadd2(ls_a, pv);
+          pk[x] = pack2<kBF16>(pv.x, pv.y);
+        }
+        tmem_st16(t_sb + q2 * 16, pk);
+      }
+      l_sum += (ls_a.x + ls_a.y) + (ls_b.x + ls_b.y);
+      if (rescale) {  // warp-uniform
+        mbar_wait(&pv_done[(j - 1) & 1], ((j - 1) >> 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int q4 = 0; q4 < D / 32; ++q4) {
+          float o[32];
+          tmem_ld32(t_o + q4 * 32, reinterpret_cast<uint32_t*>(o));
+          tc_wait_ld();
+#pragma unroll
+          for (int x = 0; x < 32; ++x) o[x] *= alpha;
+          tmem_st32(t_o + q4 * 32, reinterpret_cast<const uint32_t*>(o));
+        }
+      }
+      tc_wait_st();
+      tc_fence_before();
+      mbar_arrive(&p_ready[buf]);
+    }
+    // ------------------------------- epilogue -------------------------------
+    if (nt > 0) {
+      if (nt > 1) mbar_wait(&pv_done[(nt - 2) & 1], ((nt - 2) >> 1) & 1);
+      mbar_wait(&pv_done[(nt - 1) & 1], ((nt - 1) >> 1) & 1);
+      tc_fence_after();
+    } else {
+      mbar_wait(&q_full[0], 0);  // the Q buffer doubles as the O staging tile: its TMA load must have landed
+    }
+    const bool has_mass = l_sum > 0.f;
+    float w_cur = has_mass ? 1.f / l_sum : 0.f;
+    const float m_fin = (m_ref == -INFINITY) ? 0.f : m_ref;
+    float lse_val = has_mass ? (m_fin * c + log2f(l_sum)) * 0.6931471805599453f : -INFINITY;
+    float w_prev = 0.f;
+    const bool merge = (p.lse_prev != nullptr) && (row_l < p.n_q);
+    if (merge) {
+      const float lp = p.lse_prev[static_cast<long long>(bh) * p.lse_bh_stride + row_l];
+      const float hi = fmaxf(lp, lse_val);
+      if (hi == -INFINITY) {
+        w_prev = 0.f;
+        w_cur = 0.f;
+      } else {
+        const float e_prev = __expf(lp - hi), e_cur = __expf(lse_val - hi);
+        const float tot = e_prev + e_cur;
+        w_prev = e_prev / tot;
+        w_cur *= e_cur / tot;
+        lse_val = hi + __logf(tot);
+      }
+    }
+    const uint32_t* o_prev_row =
+        merge ? reinterpret_cast<const uint32_t*>(static_cast<const uint16_t*>(p.o_prev) +
+                                                  static_cast<long long>(bh) * p.o_bh_stride +
+                                                  static_cast<long long>(row_l) * p.d)
+              : nullptr;
+#pragma unroll
+    for (int q4 = 0; q4 < D / 32; ++q4) {
+      float o[32];
+      if (nt > 0) {
+        tmem_ld32(t_o + q4 * 32, reinterpret_cast<uint32_t*>(o));
+        tc_wait_ld();
+      } else {
+#pragma unroll
+        for (int x = 0; x < 32; ++x) o[x] = 0.f;
+      }
+      uint32_t pk[16];
+#pragma unroll
+      for (int x = 0; x < 16; ++x) {
+        float a = o[2 * x] * w_cur, b = o[2 * x + 1] * w_cur;
+        if (merge && q4 * 32 + 2 * x < p.d) {
+          const float2 pv = unpack2<kBF16>(o_prev_row[q4 * 16 + x]);
+          a = fmaf(pv.x, w_prev, a);
+          b = fmaf(pv.y, w_prev, b);
+        }
+        pk[x] = pack2<kBF16>(a, b);
+      }
+      uint8_t* sub = q_smem + (q4 >> 1) * Cfg::kQSub + row * 128;
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch) {
+        const int chunk = (q4 & 1) * 4 + ch;
+        *reinterpret_cast<uint4*>(sub + ((chunk ^ (row & 7)) << 4)) =
+            make_uint4(pk[4 * ch], pk[4 * ch + 1], pk[4 * ch + 2], pk[4 * ch + 3]);
+      }
+    }
+    if (row_l < p.n_q) p.lse[static_cast<long long>(bh) * p.lse_bh_stride + row_l] = lse_val;
+    fence_proxy_async_smem();
+    named_bar_sync(1, 128);
+    if (row == 0 && tile_row0 < p.n_q) {
+      for (int ch = 0; ch < kChunks; ++ch)
+        if (ch * 64 < p.d) tma_store_3d(&tm_o, q_smem + ch * Cfg::kQSub, ch * 64, tile_row0, bh);
+      tma_store_commit();
+      tma_store_wait_exit();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) tmem_dealloc(tmem_base, 512);
+}
+
+template <bool kBF16>
+static int launch_fwd256(const Geometry& g, const void* q, const void* k, const void* v, void* o, float* lse,
+                         const void* o_prev, const float* lse_prev, cudaStream_t stream) {
+  using Cfg = Fwd256Cfg;
+  const int elem = kBF16 ? kElemBF16 : kElemF16;
+  CUtensorMap tm_q, tm_k, tm_v, tm_o;
+  int rc;
+  if ((rc = make_tmap_3d(&tm_q, q, elem, g.d, g.n_q, g.bh, g.q_bh_stride, 64, kBM))) return rc;
+  if ((rc = make_tmap_3d(&tm_k, k, elem, g.d, g.n_kv, g.bh, g.kv_bh_stride, 64, kBN256))) return rc;
+  if ((rc = make_tmap_3d(&tm_v, v, elem, g.d, g.n_kv, g.bh, g.kv_bh_stride, 64, kBN256))) return rc;
+  if ((rc = make_tmap_3d(&tm_o, o, elem, g.d, g.n_q, g.bh, g.q_bh_stride, 64, kBM))) return rc;
+  FwdParams p = {};
+  p.lse = lse;
+  p.o_prev = o_prev;
+  p.lse_prev = lse_prev;
+  p.lse_bh_stride = g.lse_bh_stride;
+  p.o_bh_stride = g.q_bh_stride;
+  p.n_q = static_cast<int>(g.n_q);
+  p.n_kv = static_cast<int>(g.n_kv);
+  p.bh = static_cast<int>(g.bh);
+  p.causal = g.causal;
+  p.diag = g.diag;
+  p.d = g.d;
+  p.npairs = static_cast<int>((g.n_q + kBM - 1) / kBM);  // one query tile per CTA
+  p.group_log2 = sched_group_log2(g.causal != 0, p.npairs, g.bh);
+  while (((g.bh + (1ll << p.group_log2) - 1) >> p.group_log2) > 65535) ++p.group_log2;
+  p.scale_log2 = g.scale * 1.4426950408889634f;
+  auto kern = fa_fwd256_kernel<kBF16>;
+  static bool attr_set[64];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes) != cudaSuccess)
+      return FA_SM100_ELAUNCH;
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
+  }
+  const long long rank_lo = p.npairs < (1 << kRankBitsY) ? p.npairs : (1 << kRankBitsY);
+  const long long rank_hi = (p.npairs + (1 << kRankBitsY) - 1) >> kRankBitsY;
+  const long long gx = rank_hi << p.group_log2, gz = (g.bh + (1ll << p.group_log2) - 1) >> p.group_log2;
+  if (gx > 0x7fffffffll || gz > 65535) return FA_SM100_EINVAL_SHAPE;
+  const dim3 grid(static_cast<unsigned>(gx), static_cast<unsigned>(rank_lo), static_cast<unsigned>(gz));
+  kern<<<grid, kFwd256Threads, Cfg::kSmemBytes, stream>>>(tm_q, tm_k, tm_v, tm_o, p);
+  return launch_status();
+}
+
 template <int D, bool kBF16, bool kExt>
 static int launch_fwd(const Geometry& g, const ExtArgs& ext, const void* q, const void* k, const void* v, void* o,
                       float* lse, const void* o_prev, const float* lse_prev, cudaStream_t stream) {
@@ -615,6 +981,11 @@ template <bool kExt>
 static int fwd_dispatch(const Geometry& g, const ExtArgs& ext, const void* q, const void* k, const void* v, void* o,
                         float* lse, const void* o_prev, const float* lse_prev, cudaStream_t st) {
   const bool bf = g.dtype == FA_SM100_DTYPE_BF16;
+  if (g.dp == 256) {
+    if (kExt) return FA_SM100_EINVAL_HEADDIM;  // block-sparse / dropout variants stop at head dim 128
+    return bf ? launch_fwd256<true>(g, q, k, v, o, lse, o_prev, lse_prev, st)
+              : launch_fwd256<false>(g, q, k, v, o, lse, o_prev, lse_prev, st);
+  }
   if (g.dp == 128) {
     return bf ? launch_fwd<128, true, kExt>(g, ext, q, k, v, o, lse, o_prev, lse_prev, st)
               : launch_fwd<128, false, kExt>(g, ext, q, k, v, o, lse, o_prev, lse_prev, st);
@@ -628,7 +999,7 @@ static int fwd_dispatch(const Geometry& g, const ExtArgs& ext, const void* q, co
 extern "C" int fa_sm100_fwd(const fa_sm100_shape* s, const void* q, const void* k, const void* v, void* o,
                             float* lse, const void* o_prev, const float* lse_prev, void* stream) {
   fa::Geometry g;
-  int rc = fa::check_shape(s, &g);
+  int rc = fa::check_shape(s, &g, /*max_d=*/256);
   if (rc) return rc;
   if (!fa::aligned16(q) || !fa::aligned16(k) || !fa::aligned16(v) || !fa::aligned16(o) || lse == nullptr)
     return FA_SM100_EINVAL_PTR;

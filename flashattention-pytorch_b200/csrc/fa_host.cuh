@@ -58,12 +58,12 @@ struct Geometry {
   float scale;
 };
 
-inline int check_shape(const fa_sm100_shape* s, Geometry* g) {
+inline int check_shape(const fa_sm100_shape* s, Geometry* g, int max_d = 128) {
   if (!s) return FA_SM100_EINVAL_PTR;
   if (s->dtype != FA_SM100_DTYPE_F16 && s->dtype != FA_SM100_DTYPE_BF16) return FA_SM100_EINVAL_DTYPE;
-  // any multiple of 8 up to 128: rows stay 16-byte aligned for TMA, and the tensor maps carry the true d, so the
+  // any multiple of 8 up to 128 (256 for the plain forward): rows stay 16-byte aligned for TMA, and the tensor maps carry the true d, so the
   // columns between d and the kernel variant's 64 / 128 are zero-filled on load and clipped on store (no pad copies)
-  if (s->d < 8 || s->d > 128 || (s->d % 8)) return FA_SM100_EINVAL_HEADDIM;
+  if (s->d < 8 || s->d > max_d || (s->d % 8)) return FA_SM100_EINVAL_HEADDIM;
   if (s->bh <= 0 || s->n_q <= 0 || s->n_kv <= 0) return FA_SM100_EINVAL_SHAPE;
   if (s->n_q > (1ll << 30) || s->n_kv > (1ll << 30) || s->bh > (1ll << 30)) return FA_SM100_EINVAL_SHAPE;
   if (!(s->softmax_scale > 0.f) || !std::isfinite(s->softmax_scale)) return FA_SM100_EINVAL_SCALE;
@@ -73,7 +73,7 @@ inline int check_shape(const fa_sm100_shape* s, Geometry* g) {
   g->n_q = s->n_q;
   g->n_kv = s->n_kv;
   g->d = s->d;
-  g->dp = s->d <= 64 ? 64 : 128;
+  g->dp = s->d <= 64 ? 64 : s->d <= 128 ? 128 : 256;
   g->dtype = s->dtype;
   g->causal = s->causal ? 1 : 0;
   g->diag = static_cast<int>(diag);

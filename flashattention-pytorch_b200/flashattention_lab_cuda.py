@@ -16,7 +16,8 @@ Deliberate deviations from the reference (see DESIGN.md "Deviations"):
     inverted test in ``csrc/fa1/fa1_bwd.cu:80``.
   * ``br``/``bc``/``stages`` are accepted and ignored: the kernel picks its own tcgen05 tile shapes and the result
     does not depend on them beyond rounding.
-  * fp32 inputs and ``fp8=True`` are rejected loudly (the reference's fp8 emulation is broken).
+  * fp32 inputs run in fp32 arithmetic on the CUDA cores (the reference's contract for fp32, tolerance 1e-4);
+    ``fp8=True`` is rejected loudly (the reference's fp8 emulation is broken).
   * head dims that are a multiple of 8 (<= 128) run natively; others are zero-padded to the next multiple of 8.
 
 There is NO fallback: if the shared library is missing or the device is not sm_100 every call raises.
@@ -80,6 +81,8 @@ ABI = {
     "fa_sm100_bwd_prepare": (ctypes.c_int, [_SP, _P, _P, _P, _P, _P, _P]),
     "fa_sm100_bwd": (ctypes.c_int, [_SP, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "fa_sm100_bwd_accum": (ctypes.c_int, [_SP, _P, _P, _P, _P, _P, _P, _P, _P, ctypes.c_int64, _P]),
+    "fa_sm100_fwd_f32": (ctypes.c_int, [_SP, _P, _P, _P, _P, _P, _P]),
+    "fa_sm100_bwd_f32": (ctypes.c_int, [_SP, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "fa_sm100_dq_finish": (ctypes.c_int, [_SP, _P, _P, _P]),
     "fa_sm100_cast_scaled": (ctypes.c_int, [_P, _P, ctypes.c_int64, ctypes.c_float, ctypes.c_int32, _P]),
 }
@@ -119,6 +122,7 @@ def _check(rc: int, what: str) -> None:
 
 
 _DTYPES = {torch.float16: 0, torch.bfloat16: 1}
+_F32 = 2  # FA_SM100_DTYPE_F32: only the *_f32 entry points take it
 
 
 def _dtype_code(t: torch.Tensor) -> int:
@@ -126,19 +130,24 @@ def _dtype_code(t: torch.Tensor) -> int:
         return _DTYPES[t.dtype]
     except KeyError:
         raise NotImplementedError(
-            f"flashattention_lab_cuda (sm_100a): dtype {t.dtype} is not supported; the tcgen05 path takes fp16/bf16"
+            f"flashattention_lab_cuda (sm_100a): dtype {t.dtype} is not supported; the tcgen05 path takes fp16/bf16 "
+            "(fp32 tensors go through fwd_f32_raw / bwd_f32_raw, which the six public functions pick automatically)"
         ) from None
 
 
-MAX_HEAD_DIM = 128
+MAX_HEAD_DIM = 128          # backward, fp32 and the block-sparse / dropout variants
+MAX_HEAD_DIM_FORWARD = 256  # the plain 16-bit forward has a dedicated 129..256 kernel
 
 
-def _padded_head_dim(d: int) -> int:
+def _padded_head_dim(d: int, limit: int = MAX_HEAD_DIM) -> int:
     """Head dims that are a multiple of 8 go to the kernels as they are (the TMA tensor maps carry the true d: columns
-    up to the kernel variant's 64 / 128 are zero-filled on load and clipped on store, no copies).  Other sizes — rows
-    would not be 16-byte aligned — are zero-padded to the next multiple of 8 by the shim."""
-    if d > MAX_HEAD_DIM:
-        raise NotImplementedError(f"flashattention_lab_cuda (sm_100a): head dim {d} > {MAX_HEAD_DIM} is not supported")
+    up to the kernel variant's 64 / 128 / 256 are zero-filled on load and clipped on store, no copies).  Other sizes —
+    rows would not be 16-byte aligned — are zero-padded to the next multiple of 8 by the shim."""
+    if d > limit:
+        what = "the backward pass" if limit == MAX_HEAD_DIM and d <= MAX_HEAD_DIM_FORWARD else "this path"
+        raise NotImplementedError(f"flashattention_lab_cuda (sm_100a): head dim {d} > {limit} is not supported by {what}"
+                                  + (" (the forward goes up to 256; dK and dV accumulators of 256 columns each would "
+                                     "need all of TMEM)" if what == "the backward pass" else ""))
     if os.environ.get("FA_SM100_PAD_HEAD_DIM") == "1":  # debugging aid: the round-1 behaviour (pad to 64 / 128)
         return 64 if d <= 64 else 128
     return (d + 7) // 8 * 8
@@ -203,7 +212,7 @@ def _empty_like_strided(t: torch.Tensor, dtype=None) -> torch.Tensor:
 
 
 def fwd_raw(q, k, v, causal, softmax_scale, *, q_row0=0, kv_col0=0, out=None, lse=None, merge=False):
-    """q: (bh, n_q, d), k/v: (bh, n_kv, d), d % 8 == 0, d <= 128.  Returns (o, lse).
+    """q: (bh, n_q, d), k/v: (bh, n_kv, d), d % 8 == 0, d <= 256.  Returns (o, lse).
 
     ``merge=True`` folds the new partial into the given ``out``/``lse`` by log-sum-exp (ring attention)."""
     lib = load_library()
@@ -365,6 +374,35 @@ def bwd_ex_raw(q, k, v, o, do, lse, causal, softmax_scale, *, block_mask=None, d
     return dq_finish_raw(dq_accum, q.dtype, softmax_scale), dk, dv
 
 
+def fwd_f32_raw(q, k, v, causal, softmax_scale, *, q_row0=0, kv_col0=0):
+    """fp32 tensors (d % 4 == 0, d <= 128): fp32 arithmetic on the CUDA cores, results in fp32."""
+    lib = load_library()
+    bh, n_q, d = q.shape
+    q, k, v = q.contiguous(), k.contiguous(), v.contiguous()
+    out = torch.empty_like(q)
+    lse = torch.empty((bh, n_q), device=q.device, dtype=torch.float32)
+    shape = make_shape(bh, n_q, k.shape[1], d, _F32, causal, softmax_scale, q_row0, kv_col0)
+    with torch.cuda.device(q.device):
+        _check(lib.fa_sm100_fwd_f32(ctypes.byref(shape), q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(),
+                                    lse.data_ptr(), _stream_ptr(q)), "fa_sm100_fwd_f32")
+    return out, lse
+
+
+def bwd_f32_raw(q, k, v, o, do, lse, causal, softmax_scale, *, q_row0=0, kv_col0=0):
+    lib = load_library()
+    bh, n_q, d = q.shape
+    q, k, v, o, do = (t.contiguous() for t in (q, k, v, o, do))
+    lse = lse.to(torch.float32).contiguous()
+    dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+    delta = torch.empty((bh, n_q), device=q.device, dtype=torch.float32)
+    shape = make_shape(bh, n_q, k.shape[1], d, _F32, causal, softmax_scale, q_row0, kv_col0)
+    with torch.cuda.device(q.device):
+        _check(lib.fa_sm100_bwd_f32(ctypes.byref(shape), q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(),
+                                    do.data_ptr(), lse.data_ptr(), delta.data_ptr(), dq.data_ptr(), dk.data_ptr(),
+                                    dv.data_ptr(), _stream_ptr(q)), "fa_sm100_bwd_f32")
+    return dq, dk, dv
+
+
 def dq_finish_raw(dq_accum, dtype, softmax_scale):
     lib = load_library()
     bh, n_q, d = dq_accum.shape
@@ -389,10 +427,20 @@ def cast_scaled(acc: torch.Tensor, alpha: float, dtype: torch.dtype) -> torch.Te
 # the six functions of the reference's pybind module
 # ------------------------------------------------------------------------------------------------------------------
 @torch.no_grad()  # reference csrc/fa2/fa2_fwd.cu:38 (NoGradGuard)
+def _pad4(x):
+    d = x.shape[-1]
+    return x.contiguous() if d % 4 == 0 else torch.nn.functional.pad(x, (0, 4 - d % 4)).contiguous()
+
+
 def _forward(q, k, v, causal, softmax_scale):
     _validate_qkv(q, k, v)
     d = q.shape[-1]
-    dp = _padded_head_dim(d)
+    if q.dtype == torch.float32:  # the reference's fp32 contract (csrc/fa1/fa1_fwd.cu:67): fp32 arithmetic end to end
+        if d > MAX_HEAD_DIM:
+            raise NotImplementedError(f"flashattention_lab_cuda (sm_100a): head dim {d} > {MAX_HEAD_DIM} is not supported")
+        o, lse = fwd_f32_raw(_pad4(q), _pad4(k), _pad4(v), bool(causal), float(softmax_scale))
+        return (o if d % 4 == 0 else o[..., :d].contiguous()), lse
+    dp = _padded_head_dim(d, MAX_HEAD_DIM_FORWARD)
     o, lse = fwd_raw(_pad_d(q, dp), _pad_d(k, dp), _pad_d(v, dp), bool(causal), float(softmax_scale))
     if dp != d:
         o = o[..., :d].contiguous()
@@ -407,6 +455,12 @@ def _backward(q, k, v, o, do, lse, causal, softmax_scale):
     if lse.shape != q.shape[:2]:
         raise RuntimeError("lse must be (batch*heads, seqlen)")
     d = q.shape[-1]
+    if q.dtype == torch.float32:
+        dq, dk, dv = bwd_f32_raw(_pad4(q), _pad4(k), _pad4(v), _pad4(o.float()), _pad4(do.float()), lse, bool(causal),
+                                 float(softmax_scale))
+        if d % 4:
+            dq, dk, dv = (t[..., :d].contiguous() for t in (dq, dk, dv))
+        return dq, dk, dv
     dp = _padded_head_dim(d)
     dq, dk, dv = bwd_raw(_pad_d(q, dp), _pad_d(k, dp), _pad_d(v, dp), _pad_d(o, dp), _pad_d(do.to(q.dtype), dp),
                          lse.to(torch.float32).contiguous(), bool(causal), float(softmax_scale))

@@ -30,10 +30,11 @@ extern "C" {
 
 #define FA_SM100_DTYPE_F16 0
 #define FA_SM100_DTYPE_BF16 1
+#define FA_SM100_DTYPE_F32 2 /* only for the *_f32 entry points */
 
 #define FA_SM100_OK 0
 #define FA_SM100_EINVAL_DTYPE (-1)   /* dtype is not fp16 / bf16 */
-#define FA_SM100_EINVAL_HEADDIM (-2) /* d is not a multiple of 8 in [8, 128] (the shim zero-pads d % 8 != 0) */
+#define FA_SM100_EINVAL_HEADDIM (-2) /* d is not a multiple of 8 in [8, 128] ([8, 256] for fa_sm100_fwd)    */
 #define FA_SM100_EINVAL_SHAPE (-3)   /* non-positive sizes, sizes beyond int32 tile indexing, bad strides */
 #define FA_SM100_EINVAL_PTR (-4)     /* NULL or mis-aligned tensor pointer */
 #define FA_SM100_EINVAL_SCALE (-5)   /* softmax_scale must be finite and > 0 */
@@ -47,7 +48,7 @@ typedef struct fa_sm100_shape {
   int64_t bh;            /* number of independent (batch*head) slices                                  */
   int64_t n_q;           /* query rows per slice                                                       */
   int64_t n_kv;          /* key/value rows per slice                                                   */
-  int32_t d;             /* head dim: any multiple of 8 up to 128 (rows stay 16-byte aligned)          */
+  int32_t d;             /* head dim: any multiple of 8 up to 128 (fa_sm100_fwd: up to 256)            */
   int32_t dtype;         /* FA_SM100_DTYPE_*                                                           */
   int32_t causal;        /* 0/1; key c is visible to query r iff kv_col0 + c <= q_row0 + r             */
   float softmax_scale;   /* S = Q K^T * softmax_scale                                                  */
@@ -138,6 +139,19 @@ int fa_sm100_bwd_ex(const fa_sm100_shape* s, const fa_sm100_ext* ext, const void
 int fa_sm100_bwd_accum(const fa_sm100_shape* s, const void* q, const void* k, const void* v, const void* d_o,
                        const float* rowstats, float* dq_accum, float* dk_accum, float* dv_accum,
                        int64_t acc_bh_stride, void* stream);
+
+/*
+ * fp32 inputs (BASELINE config C1; the reference up-casts everything to fp32: csrc/fa1/fa1_fwd.cu:67,79-80, and its
+ * tests hold fp32 to rtol = atol = 1e-4: tests/utils.py:31-36).  These two entry points keep that contract with plain
+ * fp32 FMA arithmetic on the CUDA cores (no tensor-core rounding): same operator, same layouts with fp32 elements,
+ * shape.dtype = FA_SM100_DTYPE_F32, d a multiple of 4 up to 128, bh <= 65535.  The backward is self-contained:
+ * `delta_ws` is a scratch of bh * n_q floats, dq / dk / dv are written in fp32 (dq is zero-filled, then accumulated
+ * with fp32 atomics, so its last bits vary from run to run).
+ */
+int fa_sm100_fwd_f32(const fa_sm100_shape* s, const float* q, const float* k, const float* v, float* o, float* lse,
+                     void* stream);
+int fa_sm100_bwd_f32(const fa_sm100_shape* s, const float* q, const float* k, const float* v, const float* o,
+                     const float* d_o, const float* lse, float* delta_ws, float* dq, float* dk, float* dv, void* stream);
 
 /* dq[i] = cast(dq_accum[i] * softmax_scale).  (The reference scales per tile: csrc/fa1/fa1_bwd.cu:102-103.) */
 int fa_sm100_dq_finish(const fa_sm100_shape* s, const float* dq_accum, void* dq, void* stream);

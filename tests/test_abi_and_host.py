@@ -20,7 +20,7 @@ def _declared_symbols(header=HEADER):
 def test_header_declares_the_expected_surface():
     syms = _declared_symbols()
     for needed in ("fa_sm100_fwd", "fa_sm100_bwd", "fa_sm100_bwd_accum", "fa_sm100_bwd_prepare", "fa_sm100_dq_finish",
-                   "fa_sm100_strerror"):
+                   "fa_sm100_fwd_ex", "fa_sm100_bwd_ex", "fa_sm100_fwd_f32", "fa_sm100_bwd_f32", "fa_sm100_strerror"):
         assert needed in syms
     assert not any("probe" in s for s in syms), "probe kernels belong to the debug library, not the product ABI"
 
@@ -74,7 +74,10 @@ def test_argument_validation_happens_before_any_cuda_call():
 
     assert fwd(dtype_code=7) == -1
     assert fwd(d=96) == 0 or fwd(d=96) <= -6  # multiples of 8 up to 128 pass validation (then fail on the fake device)
-    assert fwd(d=100) == -2 and fwd(d=136) == -2 and fwd(d=4) == -2
+    assert fwd(d=100) == -2 and fwd(d=264) == -2 and fwd(d=4) == -2
+    assert fwd(d=136) <= -6 and fwd(d=256) <= -6  # the plain forward goes up to 256
+    sb = ext.make_shape(**{**good, "d": 256})
+    assert lib.fa_sm100_bwd(ctypes.byref(sb), fake, fake, fake, fake, fake, fake, fake, fake, None) == -2
     assert fwd(n_q=0) == -3
     assert fwd(softmax_scale=0.0) == -5
     s = ext.make_shape(**good)

@@ -88,6 +88,32 @@ def test_head_dims_run_natively(d, causal):
     assert torch.equal(o2, o) and torch.equal(lse2, lse)
 
 
+@pytest.mark.parametrize("bh,n,d,dtype,causal", [(2, 333, 256, torch.bfloat16, True), (3, 1000, 256, torch.float16, False),
+                                                 (2, 2048, 256, torch.bfloat16, True), (2, 640, 160, torch.bfloat16, True),
+                                                 (1, 129, 192, torch.float16, False), (2, 64, 200, torch.bfloat16, True)])
+def test_forward_head_dims_up_to_256(bh, n, d, dtype, causal):
+    """The dedicated 129..256 forward kernel (one query tile per CTA, O in 256 TMEM columns); the backward stops at
+    128 and says so."""
+    torch.manual_seed(d + n)
+    q, k, v = (torch.randn(bh, n, d, device="cuda", dtype=dtype) for _ in range(3))
+    scale = d ** -0.5
+    o, lse = ext.forward(q, k, v, causal, scale, 64, 128)
+    from oracle.attention_oracle import dense_forward
+
+    o_r, lse_r = dense_forward(q.float().cpu(), k.float().cpu(), v.float().cpu(), causal, scale)
+    assert o.shape == q.shape and o.dtype == dtype
+    assert error_report(o, o_r, 5e-2, 5e-2)["violations"] == 0
+    assert error_report(lse, lse_r, 1e-3, 1e-3)["violations"] == 0
+    with pytest.raises(NotImplementedError, match="backward"):
+        ext.backward(q, k, v, o, torch.randn_like(o), lse, causal, scale, 64, 128)
+    # ring-style merge of two key halves through the same kernel equals the one-shot result
+    h = (n // 2 + 7) // 8 * 8
+    if 0 < h < n and not causal:
+        o1, l1 = ext.fwd_raw(q, k[:, :h].contiguous(), v[:, :h].contiguous(), False, scale)
+        ext.fwd_raw(q, k[:, h:].contiguous(), v[:, h:].contiguous(), False, scale, out=o1, lse=l1, merge=True)
+        assert (o1.float() - o.float()).abs().max() < 2e-2 and (l1 - lse).abs().max() < 1e-4
+
+
 def test_head_dim_not_a_multiple_of_8_is_padded_by_the_shim():
     torch.manual_seed(5)
     q, k, v, do = (torch.randn(2, 100, 20, device="cuda", dtype=torch.float16) for _ in range(4))
@@ -99,7 +125,7 @@ def test_head_dim_not_a_multiple_of_8_is_padded_by_the_shim():
         assert got.shape == want.shape
         assert error_report(got, want, tol, tol)["violations"] == 0, name
     with pytest.raises(NotImplementedError):
-        big = torch.randn(1, 16, 136, device="cuda", dtype=torch.float16)
+        big = torch.randn(1, 16, 264, device="cuda", dtype=torch.float16)
         ext.forward(big, big, big, False, 0.1, 128, 128)
 
 
@@ -226,7 +252,7 @@ def test_determinism_of_forward_and_dkv(c2):
 
 
 def test_errors_surface():
-    q = torch.randn(2, 64, 64, device="cuda", dtype=torch.float32)
+    q = torch.randn(2, 64, 64, device="cuda", dtype=torch.float64)
     with pytest.raises(NotImplementedError):
         ext.forward(q, q, q, False, 0.125, 128, 128)
     h = q.half()
