@@ -67,7 +67,8 @@ struct BwdParams {
   long long dq_bh_stride;
   int n_q, n_kv, bh, causal, diag, nqt, nkt, group_log2;
   int d;  // true head dim (<= D); the tensor maps zero-fill / clip the columns in [d, D)
-  int accum_kv;  // 0: dk / dv written in the input dtype   1: fp32 partials reduce-added into travelling accumulators
+  int accum_kv;  // 0: dk / dv written in the input dtype   1: fp32 partials reduce-added into given accumulators
+                 // 2: fp32 partials stored (overwriting) -- ring attention adds them to the travelling accumulators
   float scale_log2, scale;
   // ---- extended variant only (kExt): block-sparse tile mask and dropout (see fa_fwd_sm100.cu) ----
   const uint8_t* block_mask;  // (nqt, nkt) per slice or shared, nonzero = tile is computed; nullable
@@ -680,18 +681,23 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
         tma_store_commit();
         tma_store_wait_exit();  // K/V staging has been read; the stores complete by grid end
       }
-    } else if (n_iter > 0) {
-      // fp32 accumulators that travel with the K/V block (ring attention): the partial is reduce-added in fp32, 32
-      // columns (one 128-byte swizzled row per kv row, 16 KiB) at a time, D/64 such chunks per round through the
-      // same V / K buffer.  tm_dv / tm_dk describe the fp32 accumulators here.
+    } else if (n_iter > 0 || p.accum_kv == 2) {
+      // fp32 partials for ring attention (tm_dv / tm_dk describe fp32 tensors here): reduce-added into the given
+      // accumulators (mode 1) or stored (mode 2, zeros where this K/V tile saw no query), 32 columns -- one 128-byte
+      // swizzled row per kv row, 16 KiB -- at a time, D/64 such chunks per round through the same V / K buffer.
       constexpr int kPerRound = D / 64;
 #pragma unroll
       for (int round = 0; round < 2; ++round) {
 #pragma unroll
         for (int u = 0; u < kPerRound; ++u) {
           float a[32];
-          tmem_ld32(t_acc + (round * kPerRound + u) * 32, reinterpret_cast<uint32_t*>(a));
-          tc_wait_ld();
+          if (n_iter > 0) {
+            tmem_ld32(t_acc + (round * kPerRound + u) * 32, reinterpret_cast<uint32_t*>(a));
+            tc_wait_ld();
+          } else {
+#pragma unroll
+            for (int x = 0; x < 32; ++x) a[x] = 0.f;
+          }
           uint8_t* rowp = stage_tile + u * Cfg::kDqStageBytes + r * 128;
 #pragma unroll
           for (int c = 0; c < 8; ++c)
@@ -703,7 +709,9 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
         if (r == 0) {
           for (int u = 0; u < kPerRound; ++u) {
             const int col = (round * kPerRound + u) * 32;
-            if (col < p.d) tma_reduce_add_3d(tm, stage_tile + u * Cfg::kDqStageBytes, col, j * kT, bh);
+            if (col >= p.d) continue;
+            if (p.accum_kv == 2) tma_store_3d(tm, stage_tile + u * Cfg::kDqStageBytes, col, j * kT, bh);
+            else tma_reduce_add_3d(tm, stage_tile + u * Cfg::kDqStageBytes, col, j * kT, bh);
           }
           tma_store_commit();
           tma_store_wait_read<0>();
@@ -786,7 +794,7 @@ fa_bwd_prepare_kernel(const uint16_t* __restrict__ o, const uint16_t* __restrict
 
 template <int D, bool kBF16, bool kExt>
 static int launch_bwd(const Geometry& g, const ExtArgs& ext, const void* q, const void* k, const void* v,
-                      const void* d_o, const float* rowstats, float* dq_accum, void* dk, void* dv, bool accum_kv,
+                      const void* d_o, const float* rowstats, float* dq_accum, void* dk, void* dv, int accum_kv,
                       long long acc_bh_stride, cudaStream_t stream) {
   using Cfg = BwdCfg<D>;
   constexpr int kSmem = kExt ? Cfg::kSmemBytesExt : Cfg::kSmemBytes;
@@ -816,7 +824,7 @@ static int launch_bwd(const Geometry& g, const ExtArgs& ext, const void* q, cons
   p.causal = g.causal;
   p.diag = g.diag;
   p.d = g.d;
-  p.accum_kv = accum_kv ? 1 : 0;
+  p.accum_kv = accum_kv;
   p.nqt = static_cast<int>((g.n_q + kT - 1) / kT);
   p.nkt = static_cast<int>((g.n_kv + kT - 1) / kT);
   p.group_log2 = sched_group_log2(g.causal != 0, p.nkt, g.bh);
@@ -890,7 +898,7 @@ extern "C" int fa_sm100_bwd_prepare(const fa_sm100_shape* s, const void* o, cons
 
 namespace fa {
 static int bwd_dispatch(const fa_sm100_shape* s, const fa_sm100_ext* ext, const void* q, const void* k, const void* v,
-                        const void* d_o, const float* rowstats, float* dq_accum, void* dk, void* dv, bool accum_kv,
+                        const void* d_o, const float* rowstats, float* dq_accum, void* dk, void* dv, int accum_kv,
                         long long acc_bh_stride, void* stream) {
   Geometry g;
   int rc = check_shape(s, &g);
@@ -921,19 +929,20 @@ static int bwd_dispatch(const fa_sm100_shape* s, const fa_sm100_ext* ext, const 
 
 extern "C" int fa_sm100_bwd(const fa_sm100_shape* s, const void* q, const void* k, const void* v, const void* d_o,
                             const float* rowstats, float* dq_accum, void* dk, void* dv, void* stream) {
-  return fa::bwd_dispatch(s, nullptr, q, k, v, d_o, rowstats, dq_accum, dk, dv, false, 0, stream);
+  return fa::bwd_dispatch(s, nullptr, q, k, v, d_o, rowstats, dq_accum, dk, dv, 0, 0, stream);
 }
 
 extern "C" int fa_sm100_bwd_ex(const fa_sm100_shape* s, const fa_sm100_ext* ext, const void* q, const void* k,
                                const void* v, const void* d_o, const float* rowstats, float* dq_accum, void* dk,
                                void* dv, void* stream) {
-  return fa::bwd_dispatch(s, ext, q, k, v, d_o, rowstats, dq_accum, dk, dv, false, 0, stream);
+  return fa::bwd_dispatch(s, ext, q, k, v, d_o, rowstats, dq_accum, dk, dv, 0, 0, stream);
 }
 
 extern "C" int fa_sm100_bwd_accum(const fa_sm100_shape* s, const void* q, const void* k, const void* v,
                                   const void* d_o, const float* rowstats, float* dq_accum, float* dk_accum,
-                                  float* dv_accum, int64_t acc_bh_stride, void* stream) {
-  return fa::bwd_dispatch(s, nullptr, q, k, v, d_o, rowstats, dq_accum, dk_accum, dv_accum, true, acc_bh_stride, stream);
+                                  float* dv_accum, int64_t acc_bh_stride, int32_t overwrite, void* stream) {
+  return fa::bwd_dispatch(s, nullptr, q, k, v, d_o, rowstats, dq_accum, dk_accum, dv_accum, overwrite ? 2 : 1,
+                          acc_bh_stride, stream);
 }
 
 #ifdef FA_BWD_TRACE

@@ -13,7 +13,7 @@
 
 namespace fa {
 
-enum : int { kElemF16 = 0, kElemBF16 = 1, kElemF32 = 2 };
+enum : int { kElemF16 = 0, kElemBF16 = 1, kElemF32 = 2, kElemU8 = 3 };
 
 inline PFN_cuTensorMapEncodeTiled_v12000 tensor_map_encoder() {
   static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
@@ -35,9 +35,10 @@ inline int make_tmap_3d(CUtensorMap* out, const void* ptr, int elem, uint64_t co
                         uint64_t slice_stride_elems, uint32_t box_cols, uint32_t box_rows) {
   auto enc = tensor_map_encoder();
   if (!enc) return FA_SM100_EDRIVER;
-  const uint64_t esz = (elem == kElemF32) ? 4 : 2;
+  const uint64_t esz = (elem == kElemF32) ? 4 : (elem == kElemU8) ? 1 : 2;
   CUtensorMapDataType dt = elem == kElemF32   ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
                            : elem == kElemBF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+                           : elem == kElemU8   ? CU_TENSOR_MAP_DATA_TYPE_UINT8
                                                : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
   cuuint64_t gdim[3] = {cols, rows, slices};
   cuuint64_t gstride[2] = {cols * esz, slice_stride_elems * esz};

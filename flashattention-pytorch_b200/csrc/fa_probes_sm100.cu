@@ -107,6 +107,85 @@ fa_probe_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
   (void)lane;
 }
 
+// e4m3 probe (modes 6, 7): one 128x128x128 kind::f8f6f4 product.  mode 6: D = A B^T (A, B K-major in smem: rows of 128
+// bytes).  mode 7: D = A B with A read from TMEM (four e4m3 per 32-bit column) and B MN-major in smem (row = k index).
+__global__ void __launch_bounds__(128, 1)
+fa_probe_fp8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
+                    const uint8_t* __restrict__ a_gmem, float* __restrict__ out, int mode) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* a_smem = smem;           // [128 rows][128 B]
+  uint8_t* b_smem = smem + 16384;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 32768);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+  const int warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(tmem_slot, 256);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t t_d = tmem_base, t_a = tmem_base + 128;
+  if (threadIdx.x == 0) {
+    mbar_arrive_expect_tx(&bars[0], 32768);
+    tma_load_3d(a_smem, &tm_a, &bars[0], 0, 0, 0);
+    tma_load_3d(b_smem, &tm_b, &bars[0], 0, 0, 0);
+  }
+  if (mode == 7) {  // thread r packs row r of A into TMEM: 128 bytes = 32 columns
+    const uint32_t* arow = reinterpret_cast<const uint32_t*>(a_gmem + threadIdx.x * 128);
+    const uint32_t lane_sel = static_cast<uint32_t>(warp * 32) << 16;
+    uint32_t w[32];
+#pragma unroll
+    for (int x = 0; x < 32; ++x) w[x] = arow[x];
+    tmem_st32(t_a + lane_sel, w);
+    tc_wait_st();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (threadIdx.x == 0) {
+    mbar_wait(&bars[0], 0);
+    tc_fence_after();
+    const uint32_t a0 = smem_u32(a_smem), b0 = smem_u32(b_smem);
+    for (int kk = 0; kk < 4; ++kk) {  // 32 K-elements per instruction
+      const uint32_t acc = kk > 0 ? 1u : 0u;
+      if (mode == 6) {
+        umma_ss_f8(t_d, umma_smem_desc(a0 + kk * 32, 16, 1024), umma_smem_desc(b0 + kk * 32, 16, 1024),
+                   umma_idesc(false, 128, 128, false, false), acc);
+      } else {
+        umma_ts_f8(t_d, t_a + kk * 8, umma_smem_desc(b0 + kk * 32 * 128, 16384, 1024),
+                   umma_idesc(false, 128, 128, false, true), acc);
+      }
+    }
+    tc_commit(&bars[1]);
+  }
+  __syncwarp();
+  mbar_wait(&bars[1], 0);
+  tc_fence_after();
+  {
+    const uint32_t lane_sel = static_cast<uint32_t>(warp * 32) << 16;
+    float* orow = out + threadIdx.x * 128;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float v[32];
+      tmem_ld32(t_d + lane_sel + q * 32, reinterpret_cast<uint32_t*>(v));
+      tc_wait_ld();
+#pragma unroll
+      for (int x = 0; x < 32; ++x) orow[q * 32 + x] = v[x];
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 256);
+}
+
 // CTA-pair probe (modes 4, 5): D[256x128] through one cta_group::2 product, the two operand paths a paired forward
 // needs.  mode 4: A, B K-major from smem (S = Q K^T: each CTA stages 128 rows of A and 64 rows of B).
 // mode 5: A from TMEM, B MN-major (O = P V: each CTA stages all 128 k-rows of its 64 output columns of B).
@@ -341,6 +420,19 @@ fa_reduce_rate_kernel(const __grid_constant__ CUtensorMap tm_acc, float* __restr
 }  // namespace fa
 
 extern "C" int fa_sm100_probe_umma(int mode, int32_t dtype, const void* a, const void* b, float* out, void* stream) {
+  if (mode == 6 || mode == 7) {  // e4m3 operands: a, b are 128 x 128 bytes
+    if (!fa::aligned16(a) || !fa::aligned16(b) || !fa::aligned16(out)) return FA_SM100_EINVAL_PTR;
+    int rc8 = fa::check_device();
+    if (rc8) return rc8;
+    CUtensorMap ta, tb;
+    if ((rc8 = fa::make_tmap_3d(&ta, a, fa::kElemU8, 128, 128, 1, 128 * 128, 128, 128))) return rc8;
+    if ((rc8 = fa::make_tmap_3d(&tb, b, fa::kElemU8, 128, 128, 1, 128 * 128, 128, 128))) return rc8;
+    const int smem8 = 32768 + 1024 + 64;
+    cudaFuncSetAttribute(fa::fa_probe_fp8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem8);
+    fa::fa_probe_fp8_kernel<<<1, 128, smem8, static_cast<cudaStream_t>(stream)>>>(ta, tb, static_cast<const uint8_t*>(a),
+                                                                                 out, mode);
+    return fa::launch_status();
+  }
   if (dtype != FA_SM100_DTYPE_F16 && dtype != FA_SM100_DTYPE_BF16) return FA_SM100_EINVAL_DTYPE;
   if (mode < 0 || mode > 5) return FA_SM100_EINVAL_SHAPE;
   if (!fa::aligned16(a) || !fa::aligned16(b) || !fa::aligned16(out)) return FA_SM100_EINVAL_PTR;

@@ -269,6 +269,32 @@ __device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64
       : "memory");
 }
 
+// kind::f8f6f4 with e4m3 operands (fp32 accumulate): one instruction contracts 32 K-elements = 32 bytes, so K-major
+// operands advance by the same 32 bytes per instruction as 16-bit ones, MN-major ones by 32 rows.  The instruction
+// descriptor's format fields are 0 for e4m3, i.e. umma_idesc(false, ...) is the right descriptor.
+__device__ __forceinline__ void umma_ss_f8(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                           uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_ts_f8(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                           uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], [%1], %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
 // ------------------------------------------------------------------------------------------------
 // CTA-pair (cta_group::2) forms.  A cluster of two CTAs on one TPC shares one MMA: the leader (cluster rank 0) issues
 // it with M = 256; each CTA supplies its own 128 rows of A (smem or TMEM), N/2 rows of B in its own smem at the same
@@ -478,6 +504,14 @@ __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
   }
   return r;
 }
+// four fp32 -> one 32-bit word of four e4m3 (round to nearest even, saturating at +-448); `a` lands in the lowest byte
+__device__ __forceinline__ uint32_t pack4_e4m3(float a, float b, float c, float d) {
+  uint16_t lo, hi;
+  asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(lo) : "f"(b), "f"(a));
+  asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(hi) : "f"(d), "f"(c));
+  return static_cast<uint32_t>(lo) | (static_cast<uint32_t>(hi) << 16);
+}
+
 template <bool kBF16>
 __device__ __forceinline__ float2 unpack2(uint32_t w) {
   if constexpr (kBF16) {

@@ -19,10 +19,11 @@ merged inside the forward kernel's epilogue (``merge=True``).  Non-causal attent
 [all local q] x [visiting block].
 
 Backward: dQ accumulates locally in fp32.  The dK/dV of a K/V block accumulate in fp32 buffers that TRAVEL with the
-block, and the kernel reduce-adds its partials straight into them (``dk_accum``/``dv_accum``: no 16-bit rounding of
-partials, no separate add pass).  Each block is handled as two key halves (chunk a / chunk b) with their own
-accumulators and launches, so an accumulator posted by the previous rank after ITS first-half launch has half a step
-to cross NVLink before this rank needs it: the transfer stays off the critical path.
+block.  Each step is one launch that writes this rank's partial in fp32 (``dk_accum``/``dv_accum`` in overwrite mode:
+no 16-bit rounding); the accumulators, which cross NVLink while that launch runs, take the partial with one fp32 add
+and move on.  (Measured alternatives, profiles/r02i: letting the kernel reduce-add straight into the travelling
+buffers needs them to have arrived before the launch; splitting every block into two key halves with their own launches
+buys that slack but doubles the launches -- 6576 vs 7584 TFLOP/s at 8 GPUs for the one-launch schedule.)
 
 The schedule is written once as a generator that yields its communication requests, so the same code runs
   * under ``torch.distributed`` (``SymmMemRingDriver``: copy-engine peer copies out of symmetric memory over NVLink, the
@@ -81,8 +82,9 @@ class BlockOps:
 
     fwd: Callable      # (q, k, v, causal, scale, *, q_row0, kv_col0, out, lse, merge) -> (out, lse)
     prepare: Callable  # (o, do, lse) -> rowstats
-    bwd: Callable      # (q, k, v, o, do, lse, causal, scale, *, q_row0, kv_col0, rowstats, dq_accum, dk_accum, dv_accum)
-    #                    adds the fp32 partials into dq_accum / dk_accum / dv_accum
+    bwd: Callable      # (q, k, v, o, do, lse, causal, scale, *, q_row0, kv_col0, rowstats, dq_accum, dk_accum, dv_accum,
+    #                    accum_overwrite): adds the fp32 dQ partial into dq_accum; dK/dV partials are added into (or,
+    #                    with accum_overwrite, stored to) dk_accum / dv_accum
     finish: Callable   # (dq_accum, dtype, scale) -> dq
 
 
@@ -139,54 +141,49 @@ def ring_forward(ops: BlockOps, rank: int, world: int, q, k, v, causal: bool, sc
 
 
 def ring_backward(ops: BlockOps, rank: int, world: int, q, k, v, o, lse, do, causal: bool, scale: float) -> Coroutine:
-    """Returns (dq, dk, dv) for the local rows.  dQ accumulates locally in fp32; each K/V block travels with fp32 dK/dV
-    accumulators (one pair per key half) that every rank's kernel adds into, and is home, complete, after ``world``
-    hops."""
+    """Returns (dq, dk, dv) for the local rows.  dQ accumulates locally in fp32.  Every step is ONE launch that stores
+    this rank's dK/dV partial of the visiting block in fp32 (no 16-bit rounding); the block's fp32 accumulators, which
+    arrive from the previous rank while that launch runs, take the partial and move on, so each block is home again,
+    complete, after ``world`` hops."""
     _check_local(q, k, v, causal)
     bh, n_local, d = q.shape
     c = n_local // 2
     dq_acc = torch.empty(q.shape, device=q.device, dtype=torch.float32)
     stats_all = ops.prepare(o, do, lse, zero=dq_acc)
     stats_b = ops.prepare(o[:, c:], do[:, c:], lse[:, c:]) if causal else None
-    halves = (slice(0, c), slice(c, n_local))
     kv = [k, v]
-    # acc[g] = [dK, dV] of key half g of the block being visited; ours start at zero and come home after `world` hops
-    acc = [[torch.zeros((bh, c, d), device=k.device, dtype=torch.float32) for _ in range(2)] for _ in range(2)]
-    acc_handle = [None, None]
+    acc = None
+    acc_handle = None
     for step in range(world):
         kv_handle = None
         if step + 1 < world:
             kv_handle = yield ("post", kv)
         src = (rank - step) % world
         kb, vb = kv
-        for g, rows in enumerate(halves):
-            if acc_handle[g] is not None:  # accumulators of this half arrive from the previous rank
-                acc[g] = yield ("wait", acc_handle[g])
-            kw = dict(dk_accum=acc[g][0], dv_accum=acc[g][1])
-            kg, vg = kb[:, rows], vb[:, rows]
-            if not causal:
-                ops.bwd(q, kg, vg, None, do, None, False, scale, rowstats=stats_all, dq_accum=dq_acc, **kw)
-            elif src == rank:
-                if g == 0:  # all local rows x chunk a: causal in local indices (chunk b sees every key of chunk a)
-                    ops.bwd(q, kg, vg, None, do, None, True, scale, rowstats=stats_all, dq_accum=dq_acc, **kw)
-                else:       # chunk b x chunk b: the diagonal block
-                    ops.bwd(q[:, c:], kg, vg, None, do[:, c:], None, True, scale, rowstats=stats_b,
-                            dq_accum=dq_acc[:, c:], **kw)
-            elif src < rank:
-                if g == 0:  # every local row sees all of chunk a of an earlier rank; its chunk b is invisible
-                    ops.bwd(q, kg, vg, None, do, None, False, scale, rowstats=stats_all, dq_accum=dq_acc, **kw)
-            else:           # only chunk b sees a later rank's keys, and it sees both halves
-                ops.bwd(q[:, c:], kg, vg, None, do[:, c:], None, False, scale, rowstats=stats_b,
-                        dq_accum=dq_acc[:, c:], **kw)
-            acc_handle[g] = yield ("post", acc[g])  # they move on with their block (the last hop brings ours home)
+        rows = slice(0, c) if (causal and src < rank) else slice(None)  # key rows of the block this rank can see
+        part = [torch.empty(kb[:, rows].shape, device=k.device, dtype=torch.float32) for _ in range(2)]
+        kw = dict(dk_accum=part[0], dv_accum=part[1], accum_overwrite=True)
+        if not causal:
+            ops.bwd(q, kb, vb, None, do, None, False, scale, rowstats=stats_all, dq_accum=dq_acc, **kw)
+        elif src == rank:  # own block: the local rows are causally ordered as they lie
+            ops.bwd(q, kb, vb, None, do, None, True, scale, rowstats=stats_all, dq_accum=dq_acc, **kw)
+        elif src < rank:   # every local row sees all of chunk a of an earlier rank; its chunk b is invisible
+            ops.bwd(q, kb[:, :c], vb[:, :c], None, do, None, False, scale, rowstats=stats_all, dq_accum=dq_acc, **kw)
+        else:              # only chunk b sees a later rank's keys, and it sees both of its chunks
+            ops.bwd(q[:, c:], kb, vb, None, do[:, c:], None, False, scale, rowstats=stats_b, dq_accum=dq_acc[:, c:],
+                    **kw)
+        if acc_handle is None:
+            acc = part  # step 0 works on the rank's own block: its accumulators start as this partial
+        else:           # accumulators of the block we are working on arrive from the previous rank
+            acc = yield ("wait", acc_handle)
+            acc[0][:, rows] += part[0]
+            acc[1][:, rows] += part[1]
+        acc_handle = yield ("post", acc)  # they move on with their block (the last hop brings ours home)
         if kv_handle is not None:
             kv = yield ("wait", kv_handle)
-    for g in range(2):
-        acc[g] = yield ("wait", acc_handle[g])
+    acc = yield ("wait", acc_handle)
     dq = ops.finish(dq_acc, q.dtype, scale)
-    dk = torch.cat([acc[0][0], acc[1][0]], dim=1).to(k.dtype)
-    dv = torch.cat([acc[0][1], acc[1][1]], dim=1).to(v.dtype)
-    return dq, dk, dv
+    return dq, acc[0].to(k.dtype), acc[1].to(v.dtype)
 
 
 # ----------------------------------------------------------------------------------------------------------------------

@@ -16,8 +16,9 @@ Deliberate deviations from the reference (see DESIGN.md "Deviations"):
     inverted test in ``csrc/fa1/fa1_bwd.cu:80``.
   * ``br``/``bc``/``stages`` are accepted and ignored: the kernel picks its own tcgen05 tile shapes and the result
     does not depend on them beyond rounding.
-  * fp32 inputs run in fp32 arithmetic on the CUDA cores (the reference's contract for fp32, tolerance 1e-4);
-    ``fp8=True`` is rejected loudly (the reference's fp8 emulation is broken).
+  * fp32 inputs run in fp32 arithmetic on the CUDA cores (the reference's contract for fp32, tolerance 1e-4).
+  * ``fp8=True`` (FA3) runs a real e4m3 tensor-core forward (head dim 128); the reference only emulates fp8, and that
+    emulation is numerically broken, so parity is against this repo's own quantise -> dequantise oracle.
   * head dims that are a multiple of 8 (<= 128) run natively; others are zero-padded to the next multiple of 8.
 
 There is NO fallback: if the shared library is missing or the device is not sm_100 every call raises.
@@ -80,9 +81,12 @@ ABI = {
     "fa_sm100_rowstats_bytes": (ctypes.c_size_t, [_SP]),
     "fa_sm100_bwd_prepare": (ctypes.c_int, [_SP, _P, _P, _P, _P, _P, _P]),
     "fa_sm100_bwd": (ctypes.c_int, [_SP, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
-    "fa_sm100_bwd_accum": (ctypes.c_int, [_SP, _P, _P, _P, _P, _P, _P, _P, _P, ctypes.c_int64, _P]),
+    "fa_sm100_bwd_accum": (ctypes.c_int, [_SP, _P, _P, _P, _P, _P, _P, _P, _P, ctypes.c_int64, ctypes.c_int32, _P]),
     "fa_sm100_fwd_f32": (ctypes.c_int, [_SP, _P, _P, _P, _P, _P, _P]),
     "fa_sm100_bwd_f32": (ctypes.c_int, [_SP, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "fa_sm100_fp8_quantize": (ctypes.c_int, [_P, _P, _P, ctypes.c_int64, ctypes.c_int64, ctypes.c_int32, ctypes.c_int64,
+                                             ctypes.c_int32, ctypes.c_int32, ctypes.c_uint64, _P]),
+    "fa_sm100_fwd_fp8": (ctypes.c_int, [_SP, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "fa_sm100_dq_finish": (ctypes.c_int, [_SP, _P, _P, _P]),
     "fa_sm100_cast_scaled": (ctypes.c_int, [_P, _P, ctypes.c_int64, ctypes.c_float, ctypes.c_int32, _P]),
 }
@@ -255,14 +259,14 @@ def bwd_prepare_raw(o, do, lse, zero=None):
 
 
 def bwd_raw(q, k, v, o, do, lse, causal, softmax_scale, *, q_row0=0, kv_col0=0, rowstats=None, dq_accum=None,
-            dk_accum=None, dv_accum=None):
+            dk_accum=None, dv_accum=None, accum_overwrite=False):
     """Backward (d % 8 == 0, d <= 128).
 
     Plain call: returns (dq, dk, dv) in the input dtype.
     Ring call (``dq_accum`` fp32 with q's shape AND strides given, ``rowstats`` from ``bwd_prepare_raw``): dQ partials
     are added into ``dq_accum`` (finish with ``dq_finish_raw`` after the last step); returns (None, dk, dv) of THIS
-    K/V block (``o``/``lse`` may then be None).  With ``dk_accum``/``dv_accum`` (fp32, k's shape) the dK/dV partials are
-    reduce-added into them in fp32 by the kernel instead, and (None, None, None) is returned."""
+    K/V block (``o``/``lse`` may then be None).  With ``dk_accum``/``dv_accum`` (fp32, k's shape) the dK/dV partials go to
+    them in fp32 instead — reduce-added, or stored with ``accum_overwrite=True`` — and (None, None, None) is returned."""
     lib = load_library()
     bh, n_q, d = q.shape
     n_kv = k.shape[1]
@@ -290,7 +294,8 @@ def bwd_raw(q, k, v, o, do, lse, causal, softmax_scale, *, q_row0=0, kv_col0=0, 
         with torch.cuda.device(q.device):
             _check(lib.fa_sm100_bwd_accum(ctypes.byref(shape), q.data_ptr(), k.data_ptr(), v.data_ptr(), do.data_ptr(),
                                           rowstats.data_ptr(), dq_accum.data_ptr(), dk_accum.data_ptr(),
-                                          dv_accum.data_ptr(), _same_stride(dk_accum, dv_accum), _stream_ptr(q)),
+                                          dv_accum.data_ptr(), _same_stride(dk_accum, dv_accum),
+                                          1 if accum_overwrite else 0, _stream_ptr(q)),
                    "fa_sm100_bwd_accum")
         return None, None, None
     dk = _empty_like_strided(k)
@@ -403,6 +408,43 @@ def bwd_f32_raw(q, k, v, o, do, lse, causal, softmax_scale, *, q_row0=0, kv_col0
     return dq, dk, dv
 
 
+FP8_SEED = 0  # the reference's incoherent-processing seed (src/fa3/torch/impl.py:123: seed=0)
+
+
+def fp8_quantize_raw(x, hadamard, seed=FP8_SEED):
+    """x: (bh, n, 128) fp16/bf16 -> (e4m3 bytes as a uint8 tensor (bh, n, 128), fp32 scales (bh, ceil(n/128)))."""
+    lib = load_library()
+    bh, n, d = x.shape
+    if d != 128:
+        raise NotImplementedError("the FP8 path supports head dim 128 only")
+    x = x.contiguous()
+    out = torch.empty((bh, n, d), device=x.device, dtype=torch.uint8)
+    scales = torch.empty((bh, (n + 127) // 128), device=x.device, dtype=torch.float32)
+    with torch.cuda.device(x.device):
+        _check(lib.fa_sm100_fp8_quantize(x.data_ptr(), out.data_ptr(), scales.data_ptr(), bh, n, d, 0, _dtype_code(x),
+                                         1 if hadamard else 0, int(seed), _stream_ptr(x)), "fa_sm100_fp8_quantize")
+    return out, scales
+
+
+def fwd_fp8_raw(q, k, v, causal, softmax_scale, seed=FP8_SEED):
+    """FP8 forward: quantise (Q, K with the Hadamard rotation; V plain) and run both products in e4m3 on the tensor
+    cores.  q, k, v: (bh, n, 128) fp16/bf16.  Returns (o in q's dtype, lse fp32)."""
+    lib = load_library()
+    bh, n_q, d = q.shape
+    q8, sq = fp8_quantize_raw(q, True, seed)
+    k8, sk = fp8_quantize_raw(k, True, seed)
+    v8, sv = fp8_quantize_raw(v, False)
+    sv_ref = sv.amax(dim=1).contiguous()
+    o = torch.empty_like(q, memory_format=torch.contiguous_format)
+    lse = torch.empty((bh, n_q), device=q.device, dtype=torch.float32)
+    shape = make_shape(bh, n_q, k.shape[1], d, _dtype_code(q), causal, softmax_scale)
+    with torch.cuda.device(q.device):
+        _check(lib.fa_sm100_fwd_fp8(ctypes.byref(shape), q8.data_ptr(), k8.data_ptr(), v8.data_ptr(), sq.data_ptr(),
+                                    sk.data_ptr(), sv.data_ptr(), sv_ref.data_ptr(), o.data_ptr(), lse.data_ptr(),
+                                    _stream_ptr(q)), "fa_sm100_fwd_fp8")
+    return o, lse
+
+
 def dq_finish_raw(dq_accum, dtype, softmax_scale):
     lib = load_library()
     bh, n_q, d = dq_accum.shape
@@ -485,19 +527,17 @@ def backward(q, k, v, o, do, lse, causal, softmax_scale, br, bc):
     return _backward(q, k, v, o, do, lse, causal, softmax_scale)
 
 
-def _reject_fp8(fp8):
-    if fp8:
-        raise NotImplementedError(
-            "fp8=True: the reference's fp8 emulation is numerically broken (SURVEY.md D5) and has no pinned parity; "
-            "a real e4m3 tcgen05 path is a later row of the scope table"
-        )
-
-
 def fa3_forward(q, k, v, causal, softmax_scale, br, bc, stages, fp8):
-    _reject_fp8(fp8)
+    if fp8:  # real e4m3 path (the reference only emulates it, src/fa3/torch/impl.py:123-131); head dim 128, 16-bit inputs
+        _validate_qkv(q, k, v)
+        if q.shape[-1] != 128 or q.dtype not in _DTYPES:
+            raise NotImplementedError("fp8=True needs fp16/bf16 inputs with head dim 128")
+        with torch.no_grad():
+            return fwd_fp8_raw(q, k, v, bool(causal), float(softmax_scale))
     return _forward(q, k, v, causal, softmax_scale)
 
 
 def fa3_backward(q, k, v, o, do, lse, causal, softmax_scale, br, bc, stages, fp8):
-    _reject_fp8(fp8)
+    # fp8=True: the forward ran in e4m3; gradients are taken through the 16-bit kernels on the original q, k, v with the
+    # forward's o / lse (straight-through, as the reference's fa3_backward does: csrc/fa3/fa3_bwd.cu ignores fp8)
     return _backward(q, k, v, o, do, lse, causal, softmax_scale)

@@ -49,6 +49,14 @@ def _stream(t: torch.Tensor) -> int:
 
 def probe_umma(mode: int, a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     lib = load_library()
+    if int(mode) in (6, 7):  # e4m3 operands
+        if a.dtype != torch.float8_e4m3fn or tuple(a.shape) != (128, 128) or tuple(b.shape) != (128, 128):
+            raise ValueError("probe_umma modes 6/7: need float8_e4m3fn a, b of shape [128,128]")
+        out = torch.empty((128, 128), device=a.device, dtype=torch.float32)
+        with torch.cuda.device(a.device):
+            _check(lib.fa_sm100_probe_umma(int(mode), 0, a.data_ptr(), b.data_ptr(), out.data_ptr(), _stream(a)),
+                   "fa_sm100_probe_umma")
+        return out
     rows = 256 if int(mode) >= 4 else 128  # modes 4/5 drive a CTA pair: A and out have 256 rows
     if tuple(a.shape) != (rows, 128) or tuple(b.shape) != (128, 128) or not (a.is_contiguous() and b.is_contiguous()):
         raise ValueError(f"probe_umma mode {mode}: need contiguous a [{rows},128] and b [128,128]")

@@ -132,13 +132,14 @@ int fa_sm100_bwd_ex(const fa_sm100_shape* s, const fa_sm100_ext* ext, const void
                     const void* d_o, const float* rowstats, float* dq_accum, void* dk, void* dv, void* stream);
 
 /*
- * Ring-attention form of the main pass: instead of writing dk / dv, the fp32 partials (dK already scaled) are
- * reduce-added into `dk_accum` / `dv_accum`, fp32 (bh, n_kv, d) with slice stride `acc_bh_stride` elements (0 =>
- * n_kv * d) -- the accumulators that travel around the ring with their K/V block.  No 16-bit rounding of partials.
+ * Ring-attention form of the main pass: instead of writing 16-bit dk / dv, the fp32 partials (dK already scaled) go to
+ * `dk_accum` / `dv_accum`, fp32 (bh, n_kv, d) with slice stride `acc_bh_stride` elements (0 => n_kv * d): reduce-added
+ * (overwrite = 0) or stored (overwrite = 1: every element is written, zeros where a K/V row saw no query).  No 16-bit
+ * rounding of partials; the ring schedule adds them to the fp32 accumulators that travel with the K/V block.
  */
 int fa_sm100_bwd_accum(const fa_sm100_shape* s, const void* q, const void* k, const void* v, const void* d_o,
                        const float* rowstats, float* dq_accum, float* dk_accum, float* dv_accum,
-                       int64_t acc_bh_stride, void* stream);
+                       int64_t acc_bh_stride, int32_t overwrite, void* stream);
 
 /*
  * fp32 inputs (BASELINE config C1; the reference up-casts everything to fp32: csrc/fa1/fa1_fwd.cu:67,79-80, and its
@@ -152,6 +153,20 @@ int fa_sm100_fwd_f32(const fa_sm100_shape* s, const float* q, const float* k, co
                      void* stream);
 int fa_sm100_bwd_f32(const fa_sm100_shape* s, const float* q, const float* k, const float* v, const float* o,
                      const float* d_o, const float* lse, float* delta_ws, float* dq, float* dk, float* dv, void* stream);
+
+/*
+ * FP8 forward (the path behind the reference's fp8=True flag, src/fa3/op.py:7,
+ * src/fa3/cuda/impl.py:40-55, whose torch emulation is src/fa3/torch/impl.py:20-72,123-131).  Head dim 128 only.
+ *   fa_sm100_fp8_quantize: x (bh, n, 128) fp16/bf16 -> out8 (bh, n, 128) e4m3 bytes (dense) + one fp32 scale per
+ *     128-row block in scales[bh * ceil(n/128)]; with `hadamard` the rows are first sign-flipped (Philox bits of `seed`),
+ *     Walsh-Hadamard transformed and divided by sqrt(128) -- apply it to Q and K with the SAME seed, not to V.
+ *   fa_sm100_fwd_fp8: both products on `tcgen05.mma kind::f8f6f4`; o in shape.dtype, lse fp32.  sv_ref[bh] must be
+ *     the largest V scale of the slice (V's per-block scale is folded into the e4m3 probabilities relative to it).
+ */
+int fa_sm100_fp8_quantize(const void* x, void* out8, float* scales, int64_t bh, int64_t n, int32_t d,
+                          int64_t x_bh_stride, int32_t dtype, int32_t hadamard, uint64_t seed, void* stream);
+int fa_sm100_fwd_fp8(const fa_sm100_shape* s, const void* q8, const void* k8, const void* v8, const float* sq,
+                     const float* sk, const float* sv, const float* sv_ref, void* o, float* lse, void* stream);
 
 /* dq[i] = cast(dq_accum[i] * softmax_scale).  (The reference scales per tile: csrc/fa1/fa1_bwd.cu:102-103.) */
 int fa_sm100_dq_finish(const fa_sm100_shape* s, const float* dq_accum, void* dq, void* stream);

@@ -21,6 +21,8 @@ extern "C" {
  * CTA-pair forms (cluster of 2, cta_group::2, M = 256; a and out have 256 rows, b stays 128x128):
  *                         4: D = A B^T (A,B K-major smem, B rows split across the pair)
  *                         5: D = A B (A from TMEM, B MN-major, B columns split across the pair)
+ * e4m3 forms (kind::f8f6f4; a, b are 128x128 BYTES of e4m3, `dtype` is ignored):
+ *                         6: D = A B^T (A, B K-major smem)   7: D = A B (A from TMEM, B MN-major smem)
  */
 int fa_sm100_probe_umma(int mode, int32_t dtype, const void* a, const void* b, float* out, void* stream);
 

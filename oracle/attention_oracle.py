@@ -321,3 +321,44 @@ def dense_ext_backward_fp32(q, k, v, do, causal=False, softmax_scale=None, block
     dk = torch.matmul(ds.transpose(-2, -1), qf) * softmax_scale
     return dq, dk, dv, o, lse
 
+
+# ----------------------------------------------------------------------------------------------------------------------
+# FP8 forward
+# ----------------------------------------------------------------------------------------------------------------------
+def fp8_quantize_dequantize(x, hadamard, seed=0, block=128):
+    """What the kernels' quantisation pre-pass does to a (bh, n, 128) tensor, returned DE-quantised in fp32 (plus the
+    e4m3 tensor and the per-block scales): optional incoherent processing as the reference's emulation
+    (src/fa3/torch/impl.py:41-59: random sign flip, Walsh-Hadamard transform, 1/sqrt(d)) with signs from Philox bits of
+    ``seed``; then per-``block``-rows absmax / 448 scales (:20-31) and round-to-nearest e4m3 (torch.float8_e4m3fn)."""
+    xf = x.float().cpu()
+    bh, n, d = xf.shape
+    if hadamard:
+        lanes = torch.arange(d // 4, dtype=torch.int64)
+        zero = torch.zeros_like(lanes)
+        words = philox4x32_7(lanes, zero, zero, zero, int(seed) & _U32, (int(seed) >> 32) & _U32)
+        bits = torch.stack(words, dim=-1).reshape(-1) & 1  # element 4 * lane + i takes word i of lane's call
+        xf = xf * (1.0 - 2.0 * bits.float())
+        h = 1
+        while h < d:
+            y = xf.reshape(bh, n, d // (2 * h), 2, h)
+            xf = torch.stack((y[..., 0, :] + y[..., 1, :], y[..., 0, :] - y[..., 1, :]), dim=-2).reshape(bh, n, d)
+            h *= 2
+        xf = xf * (d ** -0.5)
+    nb = (n + block - 1) // block
+    pad = nb * block - n
+    xp = torch.nn.functional.pad(xf, (0, 0, 0, pad)).reshape(bh, nb, block * d)
+    amax = xp.abs().amax(dim=-1)
+    scale = torch.where(amax > 0, amax / 448.0, torch.ones_like(amax))
+    q8 = (xp / scale[..., None]).to(torch.float8_e4m3fn)
+    deq = (q8.float() * scale[..., None]).reshape(bh, nb * block, d)[:, :n]
+    return deq, q8.reshape(bh, nb * block, d)[:, :n], scale
+
+
+def fp8_forward_oracle(q, k, v, causal=False, softmax_scale=None, seed=0):
+    """fp32 attention over the quantise -> dequantise images of Q, K (rotated) and V: the target of the e4m3 kernel up
+    to its e4m3 rounding of the probabilities (not modelled here: it depends on the running row maximum)."""
+    qd, _, _ = fp8_quantize_dequantize(q, True, seed)
+    kd, _, _ = fp8_quantize_dequantize(k, True, seed)
+    vd, _, _ = fp8_quantize_dequantize(v, False)
+    return dense_forward(qd, kd, vd, causal, softmax_scale)
+

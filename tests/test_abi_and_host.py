@@ -20,7 +20,8 @@ def _declared_symbols(header=HEADER):
 def test_header_declares_the_expected_surface():
     syms = _declared_symbols()
     for needed in ("fa_sm100_fwd", "fa_sm100_bwd", "fa_sm100_bwd_accum", "fa_sm100_bwd_prepare", "fa_sm100_dq_finish",
-                   "fa_sm100_fwd_ex", "fa_sm100_bwd_ex", "fa_sm100_fwd_f32", "fa_sm100_bwd_f32", "fa_sm100_strerror"):
+                   "fa_sm100_fwd_ex", "fa_sm100_bwd_ex", "fa_sm100_fwd_f32", "fa_sm100_bwd_f32", "fa_sm100_fp8_quantize",
+                   "fa_sm100_fwd_fp8", "fa_sm100_strerror"):
         assert needed in syms
     assert not any("probe" in s for s in syms), "probe kernels belong to the debug library, not the product ABI"
 
@@ -168,8 +169,9 @@ def test_extension_module_exports_reference_names():
 
     for name in ("fa1_forward", "fa1_backward", "forward", "backward", "fa3_forward", "fa3_backward"):
         assert callable(getattr(ext, name))  # reference csrc/common/torch.extension.cpp:73-83
-    with pytest.raises(NotImplementedError):
-        ext.fa3_forward(None, None, None, False, 1.0, 128, 128, 2, True)
+    x = torch.randn(2, 16, 128)
+    with pytest.raises(RuntimeError, match="CUDA"):  # fp8=True is a real path now: CPU tensors fail like everywhere else
+        ext.fa3_forward(x, x, x, False, 1.0, 128, 128, 2, True)
 
 
 def test_product_path_never_imports_the_oracle():

@@ -36,14 +36,18 @@ def _cpu_prepare(o, do, lse, zero=None):
 
 
 def _cpu_bwd(q, k, v, o, do, lse, causal, scale, *, q_row0=0, kv_col0=0, rowstats=None, dq_accum=None,
-             dk_accum=None, dv_accum=None):
+             dk_accum=None, dv_accum=None, accum_overwrite=False):
     dq, dk, dv = blocked_backward(q, k, v, rowstats["delta_o"], do, rowstats["lse"], causal, scale, 16, 16, q_row0,
                                   kv_col0, out_dtype=torch.float32)
     dq_accum += dq / scale  # the CUDA kernel accumulates UNSCALED dQ partials; finish() applies the scale
     if dk_accum is None:
         return None, dk, dv
-    dk_accum += dk          # ring form: fp32 partials go straight into the travelling accumulators
-    dv_accum += dv
+    if accum_overwrite:     # ring form: fp32 partials, stored ...
+        dk_accum.copy_(dk)
+        dv_accum.copy_(dv)
+    else:                   # ... or added
+        dk_accum += dk
+        dv_accum += dv
     return None, None, None
 
 

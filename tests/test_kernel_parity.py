@@ -152,6 +152,20 @@ def test_prepare_zero_fill_and_kv_accumulators():
     assert (dq.float() - 2 * dq_ref.float()).abs().max() < 6e-2
     assert ((dk_acc - 1.0) / 2 - dk_ref.float()).abs().max() < 2e-2  # fp32 partials vs the bf16-rounded plain result
     assert ((dv_acc + 2.0) / 2 - dv_ref.float()).abs().max() < 2e-2
+    # overwrite mode: every element is written (garbage in, partial out), also rows no query can see under the mask
+    junk_k = torch.full((bh, n_kv, d), float("nan"), device="cuda", dtype=torch.float32)
+    junk_v = torch.full_like(junk_k, float("nan"))
+    stats = ext.bwd_prepare_raw(o, do, lse, zero=acc)
+    ext.bwd_raw(q, k, v, None, do, None, False, 0.11, rowstats=stats, dq_accum=acc, dk_accum=junk_k, dv_accum=junk_v,
+                accum_overwrite=True)
+    assert (junk_k - dk_ref.float()).abs().max() < 2e-2 and (junk_v - dv_ref.float()).abs().max() < 2e-2
+    oc, lsec = ext.fwd_raw(q, k, v, True, 0.11)  # causal, n_q < n_kv: keys past the last query get exact zeros
+    stats = ext.bwd_prepare_raw(oc, do, lsec, zero=acc)
+    junk_k.fill_(float("nan"))
+    junk_v.fill_(float("nan"))
+    ext.bwd_raw(q, k, v, None, do, None, True, 0.11, rowstats=stats, dq_accum=acc, dk_accum=junk_k, dv_accum=junk_v,
+                accum_overwrite=True)
+    assert torch.isfinite(junk_k).all() and torch.count_nonzero(junk_k[:, n_q:]) == 0 and torch.count_nonzero(junk_v[:, n_q:]) == 0
     # strided accumulators (a column block of a longer buffer) and a causal launch with offsets
     big_k = torch.zeros(bh, 2 * n_kv, d, device="cuda", dtype=torch.float32)
     big_v = torch.zeros_like(big_k)
