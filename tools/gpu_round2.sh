@@ -25,10 +25,14 @@ fi
 if want sanitize; then bash tools/gpu_sanitize.sh; fi
 if want sweep; then python tools/sweep.py --c3 --name ${tag}_sweep_records > gpurun_out/${tag}_sweep_c3.md 2> gpurun_out/${tag}_sweep.err; tail -5 gpurun_out/${tag}_sweep.err; grep -c "^|" gpurun_out/${tag}_sweep_c3.md; fi
 if want ncu; then
-  B="python bench.py --workload c2 --steps 2 --warmup 1 --sustain-seconds 0"
-  $B > gpurun_out/plain.log 2>&1 &&
-  ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${tag}_launches_bench_c2.csv $B > gpurun_out/ncu1.log 2>&1
-  $B > gpurun_out/plain2.log 2>&1 &&
-  ncu --set full --clock-control none --import-source on -k regex:fa_ -s 8 -c 4 -f -o gpurun_out/${tag}_prof $B > gpurun_out/ncu2.log 2>&1
-  tail -3 gpurun_out/ncu1.log gpurun_out/ncu2.log
+  for wl in c2 headline; do
+    B="python bench.py --workload $wl --steps 2 --warmup 1 --sustain-seconds 0"
+    $B > gpurun_out/plain_$wl.log 2>&1 &&
+    ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${tag}_launches_bench_$wl.csv $B > gpurun_out/ncu1_$wl.log 2>&1
+    $B > gpurun_out/plain2_$wl.log 2>&1 &&
+    ncu --set full --clock-control none --import-source on -k regex:fa_ -s 8 -c 4 -f -o gpurun_out/${tag}_prof_$wl $B > gpurun_out/ncu2_$wl.log 2>&1
+    tail -2 gpurun_out/ncu1_$wl.log gpurun_out/ncu2_$wl.log
+  done
 fi
+if want parity; then python tools/parity_report.py > gpurun_out/${tag}_parity_report.md 2>&1; tail -3 gpurun_out/${tag}_parity_report.md; fi
+if want sweep256; then python tools/sweep.py --algos fa2 --dtypes bf16 --head-dim 64 128 256 --seqlen 1024 4096 8192 --batch-size 4 --num-heads 16 --warmup 3 --iters 10 --name ${tag}_sweep_headdims > gpurun_out/${tag}_sweep_headdims.md 2> gpurun_out/${tag}_sweep_headdims.err; tail -3 gpurun_out/${tag}_sweep_headdims.err; grep -c "^|" gpurun_out/${tag}_sweep_headdims.md; fi

@@ -1,5 +1,6 @@
-"""Summarise an `ncu --set full` capture (gpurun_out/prof.ncu-rep) into profiles/<tag>_ncu_full_summary_bench_c2.json
-and refresh profiles/traffic.json (dram bytes per launch of the main kernels).  usage: python tools/ncu_summary.py [rep] [tag]"""
+"""Summarise an `ncu --set full` capture into profiles/<tag>_ncu_full_summary_bench_<workload>.json and refresh the
+workload's entry of profiles/traffic.json (DRAM bytes per launch of the main kernels, read by bench.py's roofline).
+usage: python tools/ncu_summary.py <rep> <tag> [workload=c2]"""
 import csv
 import io
 import json
@@ -9,7 +10,8 @@ from pathlib import Path
 
 ROOT = Path(__file__).resolve().parents[1]
 rep = sys.argv[1] if len(sys.argv) > 1 else str(ROOT / "gpurun_out" / "prof.ncu-rep")
-tag = sys.argv[2] if len(sys.argv) > 2 else "r01k"
+tag = sys.argv[2] if len(sys.argv) > 2 else "r02"
+workload = sys.argv[3] if len(sys.argv) > 3 else "c2"
 KEEP = ["sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed", "dram__bytes_read.sum",
         "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "gpu__time_duration.sum",
         "launch__block_size", "launch__grid_size", "launch__registers_per_thread", "lts__t_sector_hit_rate.pct",
@@ -64,7 +66,19 @@ for r in data:
     if rd is not None and wr is not None:
         traffic[key] = rd * mult.get(units[ix["dram__bytes_read.sum"]], 1.0) + wr * mult.get(units[ix["dram__bytes_write.sum"]], 1.0)
     summary[key] = rec
-(ROOT / "profiles" / f"{tag}_ncu_full_summary_bench_c2.json").write_text(json.dumps(summary, indent=1))
+out_name = f"{tag}_ncu_full_summary_bench_{workload}.json"
+(ROOT / "profiles" / out_name).write_text(json.dumps(summary, indent=1))
+tpath = ROOT / "profiles" / "traffic.json"
+tj = json.loads(tpath.read_text()) if tpath.exists() else {}
+entry = {"source": f"profiles/{out_name} (ncu --set full --clock-control none on `python bench.py --workload {workload} "
+                   f"--steps 2 --warmup 1 --sustain-seconds 0`, one capture, per launch)"}
+for key, val in traffic.items():
+    if "fa_bwd_kernel" in key:
+        entry["fa_bwd_kernel_dram_bytes_per_launch"] = val
+    if "fa_fwd_kernel" in key:
+        entry["fa_fwd_kernel_dram_bytes_per_launch"] = val
+tj[workload] = entry
+tpath.write_text(json.dumps(tj, indent=1))
 print(json.dumps({k: {kk: vv for kk, vv in v.items() if kk.startswith("derived") or "duration" in kk or "dram__bytes" in kk}
                   for k, v in summary.items()}, indent=1))
 print("traffic", traffic)
