@@ -12,7 +12,7 @@ from pathlib import Path
 
 ROOT = Path(__file__).resolve().parents[1]
 LIB = ROOT / "flashattention-pytorch_b200" / "libfa_sm100.so"
-KERNELS = {"fwd": "_ZN2fa13fa_fwd_kernelILi128ELb1EEE", "bwd": "_ZN2fa13fa_bwd_kernelILi128ELb1EEE"}
+KERNELS = {"fwd": "_ZN2fa13fa_fwd_kernelILi128ELb1ELb0EEE", "bwd": "_ZN2fa13fa_bwd_kernelILi128ELb1ELb0EEE"}  # D=128, bf16, dense
 CENSUS = ["UTCHMMA", "UTCBAR", "UTMALDG", "UTMASTG", "UTMAREDG", "UBLKCP", "LDTM", "STTM", "MUFU.EX2", "MUFU.LG2", "MUFU.RCP",
           "FFMA2", "FADD2", "FMUL2", "FFMA", "FMNMX", "F2FP", "SYNCS", "BAR.SYNC", "STS", "LDS", "RED", "ELECT",
           "R2UR", "WARPSYNC", "NANOSLEEP"]

@@ -105,7 +105,18 @@ def run_point(api_name, api, dtype_name, d, n, b, h, causal, warmup, iters):
         torch.autograd.backward(o, do, retain_graph=True)
         q.grad = k.grad = v.grad = None
 
-    t_b, sd_b = timeit(bwd, warmup, iters)
+    try:
+        t_b, sd_b = timeit(bwd, warmup, iters)
+    except NotImplementedError as exc:  # e.g. head dim 256: the forward exists, the backward does not
+        peak_mb = torch.cuda.max_memory_allocated() / 2 ** 20
+        row = {"api": api_name, "dtype": dtype_name, "d": d, "N": n, "B": b, "H": h, "causal": causal, "fwd_ms": t_f,
+               "bwd_ms": None, "fwd_tflops": f_fwd / t_f / 1e9, "bwd_tflops": None, "fwd_bwd_tflops": None,
+               "frac_nominal": None}
+        recs = [make_record(api_name, "forward", dtype_name, causal, n, d, b, h, t_f, sd_f, peak_mb,
+                            algorithmic_tflops=row["fwd_tflops"]),
+                make_record(api_name, "backward", dtype_name, causal, n, d, b, h, None, None, None, "unsupported",
+                            str(exc)[:200])]
+        return row, recs
     peak_mb = torch.cuda.max_memory_allocated() / 2 ** 20
     row = {"api": api_name, "dtype": dtype_name, "d": d, "N": n, "B": b, "H": h, "causal": causal, "fwd_ms": t_f,
            "bwd_ms": t_b, "fwd_tflops": f_fwd / t_f / 1e9, "bwd_tflops": 2.5 * f_fwd / t_b / 1e9,
@@ -156,6 +167,10 @@ def main():
             continue
         rows.append(row)
         records += recs
+        if row["bwd_ms"] is None:
+            print(f"| {api_name} | {dt} | {d} | {n} | {b} | {h} | {causal} | {row['fwd_ms']:.3f} | {row['fwd_tflops']:.0f} | "
+                  f"- | - | forward only | - |", flush=True)
+            continue
         print(f"| {api_name} | {dt} | {d} | {n} | {b} | {h} | {causal} | {row['fwd_ms']:.3f} | {row['fwd_tflops']:.0f} | "
               f"{row['bwd_ms']:.3f} | {row['bwd_tflops']:.0f} | {row['fwd_bwd_tflops']:.0f} | "
               f"{100 * row['frac_nominal']:.1f} |", flush=True)
