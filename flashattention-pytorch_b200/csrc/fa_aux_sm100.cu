@@ -84,7 +84,7 @@ extern "C" size_t fa_sm100_dq_accum_bytes(const fa_sm100_shape* s) {
 
 extern "C" int fa_sm100_dq_finish(const fa_sm100_shape* s, const float* dq_accum, void* dq, void* stream) {
   fa::Geometry g;
-  int rc = fa::check_shape(s, &g);
+  int rc = fa::check_shape(s, &g, /*max_d=*/256);
   if (rc) return rc;
   if (!fa::aligned16(dq_accum) || !fa::aligned16(dq)) return FA_SM100_EINVAL_PTR;
   cudaStream_t st = static_cast<cudaStream_t>(stream);

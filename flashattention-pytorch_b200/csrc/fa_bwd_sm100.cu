@@ -870,7 +870,7 @@ extern "C" size_t fa_sm100_rowstats_bytes(const fa_sm100_shape* s) {
 extern "C" int fa_sm100_bwd_prepare(const fa_sm100_shape* s, const void* o, const void* d_o, const float* lse,
                                     float* rowstats, float* dq_accum_zero, void* stream) {
   fa::Geometry g;
-  int rc = fa::check_shape(s, &g);
+  int rc = fa::check_shape(s, &g, /*max_d=*/256);
   if (rc) return rc;
   if (!fa::aligned16(o) || !fa::aligned16(d_o) || lse == nullptr || !fa::aligned16(rowstats))
     return FA_SM100_EINVAL_PTR;
@@ -887,7 +887,9 @@ extern "C" int fa_sm100_bwd_prepare(const fa_sm100_shape* s, const void* o, cons
 #define FA_LAUNCH_PREP(DD, BF)                                                                                  \
   fa::fa_bwd_prepare_kernel<DD, BF><<<static_cast<unsigned>(grid), 256, 0, st>>>(op, gp, lse, rowstats, g.n_q, g.bh, \
                                                                                   nqt, g.q_bh_stride, g.lse_bh_stride, g.d, dq_accum_zero)
-  if (g.dp == 128) {
+  if (g.dp == 256) {
+    if (bf) FA_LAUNCH_PREP(256, true); else FA_LAUNCH_PREP(256, false);
+  } else if (g.dp == 128) {
     if (bf) FA_LAUNCH_PREP(128, true); else FA_LAUNCH_PREP(128, false);
   } else {
     if (bf) FA_LAUNCH_PREP(64, true); else FA_LAUNCH_PREP(64, false);
@@ -897,14 +899,20 @@ extern "C" int fa_sm100_bwd_prepare(const fa_sm100_shape* s, const void* o, cons
 }
 
 namespace fa {
+// head dims 129..256: csrc/fa_bwd256_sm100.cu
+int bwd256_dispatch(const Geometry& g, const void* q, const void* k, const void* v, const void* d_o,
+                    const float* rowstats, float* dq_accum, void* dk, void* dv, cudaStream_t st);
+
 static int bwd_dispatch(const fa_sm100_shape* s, const fa_sm100_ext* ext, const void* q, const void* k, const void* v,
                         const void* d_o, const float* rowstats, float* dq_accum, void* dk, void* dv, int accum_kv,
                         long long acc_bh_stride, void* stream) {
   Geometry g;
-  int rc = check_shape(s, &g);
+  int rc = check_shape(s, &g, /*max_d=*/256);
   if (rc) return rc;
   ExtArgs ea;
   if ((rc = check_ext(ext, s, kMaxMaskTiles, &ea))) return rc;
+  // the ring-accumulator and block-sparse / dropout forms stop at head dim 128
+  if (g.dp == 256 && (accum_kv || ea.block_mask != nullptr || ea.drop_threshold != 0)) return FA_SM100_EINVAL_HEADDIM;
   if (!aligned16(q) || !aligned16(k) || !aligned16(v) || !aligned16(d_o) || !aligned16(rowstats) ||
       !aligned16(dq_accum) || !aligned16(dk) || !aligned16(dv))
     return FA_SM100_EINVAL_PTR;
@@ -914,6 +922,7 @@ static int bwd_dispatch(const fa_sm100_shape* s, const fa_sm100_ext* ext, const 
   }
   if ((rc = check_device())) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (g.dp == 256) return bwd256_dispatch(g, q, k, v, d_o, rowstats, dq_accum, dk, dv, st);
   const bool bf = g.dtype == FA_SM100_DTYPE_BF16;
 #define FA_BWD_GO(DD, BF, EXT) \
   launch_bwd<DD, BF, EXT>(g, ea, q, k, v, d_o, rowstats, dq_accum, dk, dv, accum_kv, acc_bh_stride, st)

@@ -417,7 +417,53 @@ fa_reduce_rate_kernel(const __grid_constant__ CUtensorMap tm_acc, float* __restr
   }
 }
 
+// MUFU rate probe: every thread runs `iters` rounds of 8 independent exp2 chains in one of three forms --
+// mode 0: ex2.approx.ftz.f32 (one result per MUFU op), 1: ex2.approx.ftz.f16x2, 2: ex2.approx.ftz.bf16x2 (two results per
+// op).  The host times the launch: results per second = threads * iters * 8 * (1 or 2) / time.
+__global__ void __launch_bounds__(256) fa_ex2_rate_kernel(int mode, int iters, float* __restrict__ sink) {
+  float acc = 0.f;
+  if (mode == 0) {
+    float x[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x[i] = -0.001f * static_cast<float>(threadIdx.x + i);
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(x[i]));
+#pragma unroll
+      for (int i = 0; i < 8; ++i) x[i] = x[i] - 1.0f;  // keep the argument in range, on the FMA pipe
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc += x[i];
+  } else {
+    uint32_t x[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x[i] = mode == 1 ? 0xB800B800u + threadIdx.x + i : 0xBF00BF00u + threadIdx.x + i;
+    for (int it = 0; it < iters; ++it) {
+      if (mode == 1) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) asm volatile("ex2.approx.f16x2 %0, %0;" : "+r"(x[i]));
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) asm volatile("ex2.approx.ftz.bf16x2 %0, %0;" : "+r"(x[i]));
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) x[i] ^= 0x80008000u;  // flip the signs back to negative arguments (ALU pipe)
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc += __uint_as_float(x[i] & 0x3FFFFFFFu);
+  }
+  if (acc == 123.456f) sink[0] = acc;  // never true: keeps the chains alive
+}
+
 }  // namespace fa
+
+extern "C" int fa_sm100_probe_ex2_rate(int mode, int iters, int ctas, float* sink, void* stream) {
+  if (mode < 0 || mode > 2 || iters <= 0 || ctas <= 0 || sink == nullptr) return FA_SM100_EINVAL_SHAPE;
+  int rc = fa::check_device();
+  if (rc) return rc;
+  fa::fa_ex2_rate_kernel<<<ctas, 256, 0, static_cast<cudaStream_t>(stream)>>>(mode, iters, sink);
+  return fa::launch_status();
+}
 
 extern "C" int fa_sm100_probe_umma(int mode, int32_t dtype, const void* a, const void* b, float* out, void* stream) {
   if (mode == 6 || mode == 7) {  // e4m3 operands: a, b are 128 x 128 bytes

@@ -139,8 +139,8 @@ def _dtype_code(t: torch.Tensor) -> int:
         ) from None
 
 
-MAX_HEAD_DIM = 128          # backward, fp32 and the block-sparse / dropout variants
-MAX_HEAD_DIM_FORWARD = 256  # the plain 16-bit forward has a dedicated 129..256 kernel
+MAX_HEAD_DIM = 128          # fp32, FP8, ring-accumulator and block-sparse / dropout forms
+MAX_HEAD_DIM_FORWARD = 256  # the plain 16-bit forward and backward have dedicated 129..256 kernels
 
 
 def _padded_head_dim(d: int, limit: int = MAX_HEAD_DIM) -> int:
@@ -148,10 +148,7 @@ def _padded_head_dim(d: int, limit: int = MAX_HEAD_DIM) -> int:
     up to the kernel variant's 64 / 128 / 256 are zero-filled on load and clipped on store, no copies).  Other sizes —
     rows would not be 16-byte aligned — are zero-padded to the next multiple of 8 by the shim."""
     if d > limit:
-        what = "the backward pass" if limit == MAX_HEAD_DIM and d <= MAX_HEAD_DIM_FORWARD else "this path"
-        raise NotImplementedError(f"flashattention_lab_cuda (sm_100a): head dim {d} > {limit} is not supported by {what}"
-                                  + (" (the forward goes up to 256; dK and dV accumulators of 256 columns each would "
-                                     "need all of TMEM)" if what == "the backward pass" else ""))
+        raise NotImplementedError(f"flashattention_lab_cuda (sm_100a): head dim {d} > {limit} is not supported by this path")
     if os.environ.get("FA_SM100_PAD_HEAD_DIM") == "1":  # debugging aid: the round-1 behaviour (pad to 64 / 128)
         return 64 if d <= 64 else 128
     return (d + 7) // 8 * 8
@@ -260,7 +257,7 @@ def bwd_prepare_raw(o, do, lse, zero=None):
 
 def bwd_raw(q, k, v, o, do, lse, causal, softmax_scale, *, q_row0=0, kv_col0=0, rowstats=None, dq_accum=None,
             dk_accum=None, dv_accum=None, accum_overwrite=False):
-    """Backward (d % 8 == 0, d <= 128).
+    """Backward (d % 8 == 0, d <= 256; the ring forms with accumulators: d <= 128).
 
     Plain call: returns (dq, dk, dv) in the input dtype.
     Ring call (``dq_accum`` fp32 with q's shape AND strides given, ``rowstats`` from ``bwd_prepare_raw``): dQ partials
@@ -503,7 +500,7 @@ def _backward(q, k, v, o, do, lse, causal, softmax_scale):
         if d % 4:
             dq, dk, dv = (t[..., :d].contiguous() for t in (dq, dk, dv))
         return dq, dk, dv
-    dp = _padded_head_dim(d)
+    dp = _padded_head_dim(d, MAX_HEAD_DIM_FORWARD)
     dq, dk, dv = bwd_raw(_pad_d(q, dp), _pad_d(k, dp), _pad_d(v, dp), _pad_d(o, dp), _pad_d(do.to(q.dtype), dp),
                          lse.to(torch.float32).contiguous(), bool(causal), float(softmax_scale))
     if dp != d:

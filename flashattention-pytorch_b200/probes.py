@@ -13,6 +13,7 @@ _P = ctypes.c_void_p
 ABI = {
     "fa_sm100_probe_umma": (ctypes.c_int, [ctypes.c_int, ctypes.c_int32, _P, _P, _P, _P]),
     "fa_sm100_probe_reduce_rate": (ctypes.c_int, [_P, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, _P]),
+    "fa_sm100_probe_ex2_rate": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, _P, _P]),
     "fa_sm100_probe_mma_rate": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, _P]),
 }
 _DTYPES = {torch.float16: 0, torch.bfloat16: 1}
@@ -86,3 +87,14 @@ def probe_reduce_rate(acc: torch.Tensor, nkt: int, flags: int = 0) -> None:
     with torch.cuda.device(acc.device):
         _check(lib.fa_sm100_probe_reduce_rate(acc.data_ptr(), acc.shape[0], acc.shape[1] // 128, int(nkt),
                                               int(flags), _stream(acc)), "fa_sm100_probe_reduce_rate")
+
+
+def probe_ex2_rate(mode: int, iters: int, ctas: int, device="cuda") -> None:
+    """Launch the MUFU exp2 rate probe on the current stream (0: f32, 1: f16x2, 2: bf16x2); the caller times it."""
+    lib = load_library()
+    dev = torch.device(device)
+    sink = torch.zeros(1, device=dev)
+    with torch.cuda.device(dev):
+        _check(lib.fa_sm100_probe_ex2_rate(int(mode), int(iters), int(ctas), sink.data_ptr(),
+                                           torch.cuda.current_stream(dev).cuda_stream), "fa_sm100_probe_ex2_rate")
+

@@ -34,7 +34,7 @@ extern "C" {
 
 #define FA_SM100_OK 0
 #define FA_SM100_EINVAL_DTYPE (-1)   /* dtype is not fp16 / bf16 */
-#define FA_SM100_EINVAL_HEADDIM (-2) /* d is not a multiple of 8 in [8, 128] ([8, 256] for fa_sm100_fwd)    */
+#define FA_SM100_EINVAL_HEADDIM (-2) /* d is not a multiple of 8 in [8, 256], or beyond what this form takes  */
 #define FA_SM100_EINVAL_SHAPE (-3)   /* non-positive sizes, sizes beyond int32 tile indexing, bad strides */
 #define FA_SM100_EINVAL_PTR (-4)     /* NULL or mis-aligned tensor pointer */
 #define FA_SM100_EINVAL_SCALE (-5)   /* softmax_scale must be finite and > 0 */
@@ -48,7 +48,8 @@ typedef struct fa_sm100_shape {
   int64_t bh;            /* number of independent (batch*head) slices                                  */
   int64_t n_q;           /* query rows per slice                                                       */
   int64_t n_kv;          /* key/value rows per slice                                                   */
-  int32_t d;             /* head dim: any multiple of 8 up to 128 (fa_sm100_fwd: up to 256)            */
+  int32_t d;             /* head dim: any multiple of 8 up to 256 (the *_ex, *_accum, *_f32 and fp8    */
+                         /* forms: up to 128 / exactly 128, see each entry)                            */
   int32_t dtype;         /* FA_SM100_DTYPE_*                                                           */
   int32_t causal;        /* 0/1; key c is visible to query r iff kv_col0 + c <= q_row0 + r             */
   float softmax_scale;   /* S = Q K^T * softmax_scale                                                  */

@@ -43,6 +43,13 @@ int fa_sm100_probe_mma_rate(int pair, int a_from_tmem, int n, int groups, int ct
  */
 int fa_sm100_probe_reduce_rate(float* acc, int slices, int nqt, int nkt, int flags, void* stream);
 
+/*
+ * MUFU exp2 rate probe: `ctas` CTAs of 256 threads each run `iters` rounds of 8 independent exp2 chains.
+ * mode 0: ex2.approx.ftz.f32   1: ex2.approx.ftz.f16x2   2: ex2.approx.ftz.bf16x2 (two results per instruction).
+ * The caller times the launch; `sink` is a one-float device buffer that is never written.
+ */
+int fa_sm100_probe_ex2_rate(int mode, int iters, int ctas, float* sink, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -78,7 +78,8 @@ def test_argument_validation_happens_before_any_cuda_call():
     assert fwd(d=100) == -2 and fwd(d=264) == -2 and fwd(d=4) == -2
     assert fwd(d=136) <= -6 and fwd(d=256) <= -6  # the plain forward goes up to 256
     sb = ext.make_shape(**{**good, "d": 256})
-    assert lib.fa_sm100_bwd(ctypes.byref(sb), fake, fake, fake, fake, fake, fake, fake, fake, None) == -2
+    assert lib.fa_sm100_bwd(ctypes.byref(sb), fake, fake, fake, fake, fake, fake, fake, fake, None) <= -6  # valid: 129..256 kernel
+    assert lib.fa_sm100_bwd_accum(ctypes.byref(sb), fake, fake, fake, fake, fake, fake, fake, fake, 0, 1, None) == -2
     assert fwd(n_q=0) == -3
     assert fwd(softmax_scale=0.0) == -5
     s = ext.make_shape(**good)

@@ -92,20 +92,20 @@ def test_head_dims_run_natively(d, causal):
                                                  (2, 2048, 256, torch.bfloat16, True), (2, 640, 160, torch.bfloat16, True),
                                                  (1, 129, 192, torch.float16, False), (2, 64, 200, torch.bfloat16, True)])
 def test_forward_head_dims_up_to_256(bh, n, d, dtype, causal):
-    """The dedicated 129..256 forward kernel (one query tile per CTA, O in 256 TMEM columns); the backward stops at
-    128 and says so."""
+    """The dedicated 129..256 kernels: forward (one query tile per CTA, O in 256 TMEM columns) and backward (64-row
+    K/V tile per CTA, dK^T / dV^T with the head dim on the TMEM lanes)."""
     torch.manual_seed(d + n)
-    q, k, v = (torch.randn(bh, n, d, device="cuda", dtype=dtype) for _ in range(3))
+    q, k, v, do = (torch.randn(bh, n, d, device="cuda", dtype=dtype) for _ in range(4))
     scale = d ** -0.5
     o, lse = ext.forward(q, k, v, causal, scale, 64, 128)
-    from oracle.attention_oracle import dense_forward
-
-    o_r, lse_r = dense_forward(q.float().cpu(), k.float().cpu(), v.float().cpu(), causal, scale)
+    dq, dk, dv = ext.backward(q, k, v, o, do, lse, causal, scale, 64, 128)
+    dq_r, dk_r, dv_r, o_r, lse_r = dense_backward_fp32(q.cpu(), k.cpu(), v.cpu(), do.cpu(), causal, scale)
     assert o.shape == q.shape and o.dtype == dtype
-    assert error_report(o, o_r, 5e-2, 5e-2)["violations"] == 0
-    assert error_report(lse, lse_r, 1e-3, 1e-3)["violations"] == 0
-    with pytest.raises(NotImplementedError, match="backward"):
-        ext.backward(q, k, v, o, torch.randn_like(o), lse, causal, scale, 64, 128)
+    for name, got, want, tol in (("o", o, o_r, 5e-2), ("lse", lse, lse_r, 1e-3), ("dq", dq, dq_r, 5e-2),
+                                 ("dk", dk, dk_r, 5e-2), ("dv", dv, dv_r, 5e-2)):
+        assert got.shape == want.shape and (name == "lse" or got.dtype == dtype)
+        rep = error_report(got, want, tol, tol)
+        assert rep["violations"] == 0, f"d={d} {name}: {rep}"
     # ring-style merge of two key halves through the same kernel equals the one-shot result
     h = (n // 2 + 7) // 8 * 8
     if 0 < h < n and not causal:
@@ -127,6 +127,9 @@ def test_head_dim_not_a_multiple_of_8_is_padded_by_the_shim():
     with pytest.raises(NotImplementedError):
         big = torch.randn(1, 16, 264, device="cuda", dtype=torch.float16)
         ext.forward(big, big, big, False, 0.1, 128, 128)
+    with pytest.raises(RuntimeError, match="head dim"):  # the ring / block-sparse forms stop at head dim 128
+        x = torch.randn(1, 128, 256, device="cuda", dtype=torch.float16)
+        ext.fwd_ex_raw(x, x, x, False, 0.1, dropout_p=0.5, seed=1)
 
 
 def test_prepare_zero_fill_and_kv_accumulators():
