@@ -50,7 +50,12 @@ constexpr float kRescaleThreshold = 8.0f;  // lazy O rescale: only when the row 
 #ifndef FA_FWD_EMU_OF8
 #define FA_FWD_EMU_OF8 0
 #endif
-constexpr int kEmuOf8 = FA_FWD_EMU_OF8;  // element pairs (of every 8) exponentiated on the FMA pipe instead of MUFU
+// Element pairs (of every 8) exponentiated on the FMA pipe (Cody-Waite + degree-3 polynomial, ex2_poly2) instead of
+// MUFU.  Off: measured on B200 (profiles/r02s_poly_exp2_fraction.log) 1 of 8 gains 5 % at d = 64 non-causal (849 -> 896
+// TFLOP/s at N = 8K, MUFU being the clear limiter there), nothing at d = 64 causal or at d = 128, 2 of 8 and more lose
+// everywhere -- and the polynomial's 7.5e-5 relative error shows up in the LSE (7e-5 instead of 1e-6).
+template <int D>
+constexpr int emu_of8() { return FA_FWD_EMU_OF8; }
 
 template <int D>
 struct FwdCfg {
@@ -404,8 +409,8 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
       const float mc = ((m_ref == -INFINITY) ? 0.f : m_ref) * c;
 
       // P = 2^(S*c - m*c), row-sum in fp32, stored 16-bit into the first 32 columns of this S buffer.
-      // MUFU (16 ex2/clk/SM) is the co-bottleneck of the tensor pipe at d=128, so kEmuOf8 of every 8 element pairs
-      // take the polynomial path on the FMA pipe instead; all arithmetic is packed fp32x2.
+      // MUFU (16 ex2/clk/SM) is the co-bottleneck of the tensor pipe, so emu_of8<D>() of every 8 element pairs take
+      // the polynomial path on the FMA pipe instead; all arithmetic is packed fp32x2.
       float2 ls_a = make_float2(0.f, 0.f), ls_b = make_float2(0.f, 0.f);
       const float2 c2 = make_float2(c, c), nmc2 = make_float2(-mc, -mc);
       const bool dropout = kExt && p.drop_threshold != 0;
@@ -427,7 +432,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
         for (int x = 0; x < 16; ++x) {
           const float2 t = ffma2(make_float2(s[q2 * 32 + 2 * x], s[q2 * 32 + 2 * x + 1]), c2, nmc2);
           float2 pv;
-          if ((x & 7) < kEmuOf8) {
+          if ((x & 7) < emu_of8<D>()) {
             pv = ex2_poly2(t);
           } else {
             pv.x = ex2(t.x);

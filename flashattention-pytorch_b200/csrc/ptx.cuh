@@ -453,9 +453,10 @@ __device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
 }
 // 2^t for a pair on the FMA/ALU pipes instead of MUFU: Cody-Waite split t = n + f (n = round(t), |f| <= 0.5),
 // degree-3 minimax for 2^f (max rel. error 7.5e-5, far below the 16-bit rounding of P), exponent spliced in with an
-// integer shift-add.  Valid for t <= 127; t is clamped at -126 (result ~1e-38, i.e. zero for the softmax).
+// integer shift-add.  Valid for t <= 127; arguments below -126 (masked scores: -inf) give exactly 0, as ex2 does.
 __device__ __forceinline__ float2 ex2_poly2(float2 t) {
   constexpr float kMagic = 12582912.f;  // 1.5 * 2^23: adding it rounds to the nearest integer in the low mantissa bits
+  const bool zx = t.x < -126.f, zy = t.y < -126.f;
   t.x = fmaxf(t.x, -126.f);
   t.y = fmaxf(t.y, -126.f);
   const float2 r = fadd2(t, make_float2(kMagic, kMagic));
@@ -464,8 +465,8 @@ __device__ __forceinline__ float2 ex2_poly2(float2 t) {
   float2 p = ffma2(f, make_float2(0.0551716685f, 0.0551716685f), make_float2(0.2426111251f, 0.2426111251f));
   p = ffma2(p, f, make_float2(0.6932609677f, 0.6932609677f));
   p = ffma2(p, f, make_float2(0.9999280572f, 0.9999280572f));
-  p.x = __int_as_float(__float_as_int(p.x) + (__float_as_int(r.x) << 23));
-  p.y = __int_as_float(__float_as_int(p.y) + (__float_as_int(r.y) << 23));
+  p.x = zx ? 0.f : __int_as_float(__float_as_int(p.x) + (__float_as_int(r.x) << 23));
+  p.y = zy ? 0.f : __int_as_float(__float_as_int(p.y) + (__float_as_int(r.y) << 23));
   return p;
 }
 
