@@ -201,7 +201,10 @@ fa_bwd256_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
           tc_commit(&bars[kB2DQFull]);
         }
         __syncwarp();
-        mbar_wait(&bars[kB2DQDrained], 1);  // ... and half 1 (S / dP of the next tile overwrite the dS operand)
+        // ... half 1: the next tile's S / dP overwrite the packed dS operand, so dQ(1) must have COMPLETED (its own
+        // commit), but its drain may still be running: S / dP do not touch the dQ columns, and the next dQ(0) is only
+        // issued after pds_ready, which the draining warpgroup signals when it is done
+        mbar_wait(&bars[kB2DQFull], 1);
       }
       tc_commit_elect(&bars[kB2AllDone]);
     }
