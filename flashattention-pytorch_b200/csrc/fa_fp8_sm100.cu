@@ -353,18 +353,47 @@ fa_fwd_fp8_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
 }
 
 // ------------------------------------------------------------------------------------------------
-// Quantisation pre-pass: one CTA per (128-row block, slice); warp w handles rows 32 w .. 32 w + 31, lane l holds head
-// dim elements 4 l .. 4 l + 3.  kHadamard: x <- H (s o x) / sqrt(128) with s = +-1 from Philox (reference
-// src/fa3/torch/impl.py:41-59: sign flip, in-place Walsh-Hadamard butterflies, 1/sqrt(d)).  Then scale = absmax / 448
-// over the block (reference :20-31), x / scale rounded to e4m3 (saturating).
+// Quantisation pre-pass (HBM-bound): one CTA of 512 threads per (128-row block, slice); warp w handles rows
+// 8 w .. 8 w + 7, lane l holds head dim elements 4 l .. 4 l + 3.  kHadamard: x <- H (s o x) / sqrt(128) with s = +-1 from
+// Philox (reference src/fa3/torch/impl.py:41-59: sign flip, Walsh-Hadamard butterflies, 1/sqrt(d); here a true WHT).
+// Then scale = absmax / 448 over the block (reference :20-31), x / scale rounded to e4m3 (saturating).
+// Two passes over the rows: the first computes the block maximum, the second RECOMPUTES the transform (the 32 KiB
+// block comes back from L1/L2) and quantises -- no shared-memory copy of the block, so many CTAs fit per SM.
 // ------------------------------------------------------------------------------------------------
 template <bool kBF16, bool kHadamard>
-__global__ void __launch_bounds__(128) fa_fp8_quant_kernel(const uint16_t* __restrict__ x, uint8_t* __restrict__ out,
+__device__ __forceinline__ void fp8_load_transform(const uint16_t* __restrict__ row_ptr, int lane, const float (&sign)[4],
+                                                   float (&v)[4]) {
+  const uint2 raw = *reinterpret_cast<const uint2*>(row_ptr + lane * 4);
+  const float2 a = unpack2<kBF16>(raw.x), b = unpack2<kBF16>(raw.y);
+  v[0] = a.x * sign[0];
+  v[1] = a.y * sign[1];
+  v[2] = b.x * sign[2];
+  v[3] = b.y * sign[3];
+  if (kHadamard) {
+    // strides 1 and 2 inside the lane, 4 .. 64 across lanes
+    const float t0 = v[0] + v[1], t1 = v[0] - v[1], t2 = v[2] + v[3], t3 = v[2] - v[3];
+    v[0] = t0 + t2;
+    v[1] = t1 + t3;
+    v[2] = t0 - t2;
+    v[3] = t1 - t3;
+#pragma unroll
+    for (int m = 1; m < 32; m <<= 1) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float other = __shfl_xor_sync(0xffffffffu, v[i], m);
+        v[i] = (lane & m) ? other - v[i] : v[i] + other;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] *= 0.08838834764831845f;  // 1 / sqrt(128)
+  }
+}
+
+template <bool kBF16, bool kHadamard>
+__global__ void __launch_bounds__(512) fa_fp8_quant_kernel(const uint16_t* __restrict__ x, uint8_t* __restrict__ out,
                                                            float* __restrict__ scales, int n, long long x_bh_stride,
                                                            int n_tiles, uint32_t seed_lo, uint32_t seed_hi) {
-  extern __shared__ float quant_smem[];  // 128 x 129 transformed values + 4 per-warp maxima
-  float (*vals)[129] = reinterpret_cast<float (*)[129]>(quant_smem);
-  float* warp_max = quant_smem + 128 * 129;
+  __shared__ float warp_max[16];
   const int tile = blockIdx.x, bh = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float sign[4] = {1.f, 1.f, 1.f, 1.f};
@@ -373,57 +402,35 @@ __global__ void __launch_bounds__(128) fa_fp8_quant_kernel(const uint16_t* __res
 #pragma unroll
     for (int i = 0; i < 4; ++i) sign[i] = (bits.w[i] & 1u) ? -1.f : 1.f;
   }
+  const uint16_t* xb = x + static_cast<long long>(bh) * x_bh_stride;
+  const int row0 = tile * 128 + warp * 8;
   float amax = 0.f;
-  for (int rr = 0; rr < 32; ++rr) {
-    const int r = tile * 128 + warp * 32 + rr;
-    float v[4] = {0.f, 0.f, 0.f, 0.f};
-    if (r < n) {
-      const uint2 raw = *reinterpret_cast<const uint2*>(x + static_cast<long long>(bh) * x_bh_stride +
-                                                        static_cast<long long>(r) * 128 + lane * 4);
-      const float2 a = unpack2<kBF16>(raw.x), b = unpack2<kBF16>(raw.y);
-      v[0] = a.x * sign[0];
-      v[1] = a.y * sign[1];
-      v[2] = b.x * sign[2];
-      v[3] = b.y * sign[3];
-      if (kHadamard) {
-        // strides 1 and 2 inside the lane, 4 .. 64 across lanes
-        float t0 = v[0] + v[1], t1 = v[0] - v[1], t2 = v[2] + v[3], t3 = v[2] - v[3];
-        v[0] = t0 + t2;
-        v[1] = t1 + t3;
-        v[2] = t0 - t2;
-        v[3] = t1 - t3;
 #pragma unroll
-        for (int m = 1; m < 32; m <<= 1) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float other = __shfl_xor_sync(0xffffffffu, v[i], m);
-            v[i] = (lane & m) ? other - v[i] : v[i] + other;
-          }
-        }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) v[i] *= 0.08838834764831845f;  // 1 / sqrt(128)
-      }
-    }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      vals[warp * 32 + rr][lane * 4 + i] = v[i];
-      amax = fmaxf(amax, fabsf(v[i]));
+  for (int rr = 0; rr < 8; ++rr) {
+    if (row0 + rr < n) {
+      float v[4];
+      fp8_load_transform<kBF16, kHadamard>(xb + static_cast<long long>(row0 + rr) * 128, lane, sign, v);
+      amax = fmaxf(amax, fmaxf(fmaxf(fabsf(v[0]), fabsf(v[1])), fmaxf(fabsf(v[2]), fabsf(v[3]))));
     }
   }
 #pragma unroll
   for (int m = 16; m > 0; m >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, m));
   if (lane == 0) warp_max[warp] = amax;
   __syncthreads();
-  amax = fmaxf(fmaxf(warp_max[0], warp_max[1]), fmaxf(warp_max[2], warp_max[3]));
+  amax = 0.f;
+#pragma unroll
+  for (int w = 0; w < 16; ++w) amax = fmaxf(amax, warp_max[w]);
   const float scale = amax > 0.f ? amax / 448.f : 1.f;
   const float inv = 1.f / scale;
   if (threadIdx.x == 0) scales[static_cast<long long>(bh) * n_tiles + tile] = scale;
-  for (int rr = 0; rr < 32; ++rr) {
-    const int r = tile * 128 + warp * 32 + rr;
-    if (r >= n) break;
-    const float* row = vals[warp * 32 + rr];
-    const uint32_t w = pack4_e4m3(row[lane * 4] * inv, row[lane * 4 + 1] * inv, row[lane * 4 + 2] * inv, row[lane * 4 + 3] * inv);
-    *reinterpret_cast<uint32_t*>(out + (static_cast<long long>(bh) * n + r) * 128 + lane * 4) = w;
+#pragma unroll
+  for (int rr = 0; rr < 8; ++rr) {
+    if (row0 + rr < n) {
+      float v[4];
+      fp8_load_transform<kBF16, kHadamard>(xb + static_cast<long long>(row0 + rr) * 128, lane, sign, v);
+      *reinterpret_cast<uint32_t*>(out + (static_cast<long long>(bh) * n + row0 + rr) * 128 + lane * 4) =
+          pack4_e4m3(v[0] * inv, v[1] * inv, v[2] * inv, v[3] * inv);
+    }
   }
 }
 
@@ -447,14 +454,8 @@ extern "C" int fa_sm100_fp8_quantize(const void* x, void* out8, float* scales, i
   const uint32_t lo = static_cast<uint32_t>(seed), hi = static_cast<uint32_t>(seed >> 32);
   const int nn = static_cast<int>(n);
   const bool bf = dtype == FA_SM100_DTYPE_BF16;
-  constexpr int kSmem = (128 * 129 + 4) * 4;
-#define FA_QUANT_GO(BF, HAD)                                                                                        \
-  do {                                                                                                              \
-    if (cudaFuncSetAttribute(fa::fa_fp8_quant_kernel<BF, HAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem) != \
-        cudaSuccess)                                                                                                \
-      return FA_SM100_ELAUNCH;                                                                                      \
-    fa::fa_fp8_quant_kernel<BF, HAD><<<grid, 128, kSmem, st>>>(xp, op, scales, nn, x_bh_stride, n_tiles, lo, hi);     \
-  } while (0)
+#define FA_QUANT_GO(BF, HAD) \
+  fa::fa_fp8_quant_kernel<BF, HAD><<<grid, 512, 0, st>>>(xp, op, scales, nn, x_bh_stride, n_tiles, lo, hi)
   if (hadamard) {
     if (bf) FA_QUANT_GO(true, true); else FA_QUANT_GO(false, true);
   } else {
