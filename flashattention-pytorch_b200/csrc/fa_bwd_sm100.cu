@@ -553,15 +553,29 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
             if (need_mask) pv[e] = (col_base + c * 32 + x >= c_min) ? pv[e] : 0.f;
             pr[c * 32 + x] = pv[e];
           }
-          if constexpr (kExt) {
-            if (dropout) {  // one Philox call covers these 4 queries (words) x 4 keys (bytes): ours is byte kv & 3
-              const uint32_t kg = static_cast<uint32_t>(p.kv_col0 + j * kT + r);
-              const uint32_t qg = static_cast<uint32_t>(p.q_row0 + i * kT + col_base + c * 32 + x4 * 4);
-              const Philox4 rr = philox4x32_7(qg >> 2, kg >> 2, static_cast<uint32_t>(bh), p.rng_offset, p.seed_lo,
-                                              p.seed_hi);
+        }
+        if constexpr (kExt) {
+          if (dropout) {
+            // One Philox call covers 4 queries (words) x 4 keys (bytes) and the four lanes of a quad are four consecutive
+            // keys (same key >> 2), so they need the SAME calls, each lane its own byte (key & 3) of every word: lane L
+            // computes the calls of query groups x4 with (x4 & 3) == (L & 3) and the words go round the quad with
+            // xor-shuffles -- 2 calls + 24 shuffles per 32 queries instead of 8 calls.
+            const uint32_t kg = static_cast<uint32_t>(p.kv_col0 + j * kT + r);
+            const uint32_t qg0 = static_cast<uint32_t>(p.q_row0 + i * kT + col_base + c * 32);
+            const uint32_t me = lane & 3, shift = (kg & 3) * 8;
 #pragma unroll
-              for (int e = 0; e < 4; ++e)
-                if (((rr.w[e] >> ((kg & 3) * 8)) & 0xFFu) < p.drop_threshold) keep[c] &= ~(1u << (x4 * 4 + e));
+            for (int jq = 0; jq < 2; ++jq) {
+              const Philox4 w = philox4x32_7((qg0 >> 2) + 4 * jq + me, kg >> 2, static_cast<uint32_t>(bh), p.rng_offset,
+                                             p.seed_lo, p.seed_hi);
+#pragma unroll
+              for (int kx = 0; kx < 4; ++kx) {  // after this sub-round: the call of query group 4 jq + (me ^ kx)
+                const uint32_t x4 = 4 * jq + (me ^ kx);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const uint32_t word = kx == 0 ? w.w[e] : __shfl_xor_sync(0xffffffffu, w.w[e], kx);
+                  if (((word >> shift) & 0xFFu) < p.drop_threshold) keep[c] &= ~(1u << (x4 * 4 + e));
+                }
+              }
             }
           }
         }

@@ -420,12 +420,31 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
         uint32_t rnd[8];  // kExt: one random word per 4 key columns (byte b = column b of the group)
         if constexpr (kExt) {
           if (dropout) {
+            // One Philox call covers 4 queries x 4 keys and this thread needs only word (query & 3) of it, so the four
+            // lanes of a quad (four consecutive query rows: same query >> 2) share the calls: lane L computes the
+            // calls of key groups g with (g & 3) == (L & 3) and the words are exchanged with three xor-shuffles per
+            // round -- in sub-round k lane L hands word ((L & 3) ^ k) to lane L ^ k, which is exactly the word that
+            // lane's query needs.  2 calls + 6 shuffles per 32 columns instead of 8 calls.
             const uint32_t qg = static_cast<uint32_t>(p.q_row0 + row_l);
             const uint32_t kg = static_cast<uint32_t>(p.kv_col0 + col0 + q2 * 32);
+            const uint32_t me = lane & 3;
+            auto pick = [](uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t i) {
+              const uint32_t lo = (i & 1) ? a1 : a0, hi = (i & 1) ? a3 : a2;
+              return (i & 2) ? hi : lo;
+            };
 #pragma unroll
-            for (int g4 = 0; g4 < 8; ++g4)
-              rnd[g4] = philox4x32_7(qg >> 2, (kg >> 2) + g4, static_cast<uint32_t>(bh), p.rng_offset, p.seed_lo,
-                                     p.seed_hi).w[qg & 3];
+            for (int jq = 0; jq < 2; ++jq) {
+              const Philox4 w = philox4x32_7(qg >> 2, (kg >> 2) + 4 * jq + me, static_cast<uint32_t>(bh), p.rng_offset,
+                                             p.seed_lo, p.seed_hi);
+              uint32_t got[4];  // got[k] = my word of the call of key group 4 jq + (me ^ k)
+#pragma unroll
+              for (int kx = 0; kx < 4; ++kx) {
+                const uint32_t give = pick(w.w[0], w.w[1], w.w[2], w.w[3], me ^ kx);
+                got[kx] = kx == 0 ? give : __shfl_xor_sync(0xffffffffu, give, kx);
+              }
+#pragma unroll
+              for (int g = 0; g < 4; ++g) rnd[4 * jq + g] = pick(got[0], got[1], got[2], got[3], me ^ g);
+            }
           }
         }
 #pragma unroll
