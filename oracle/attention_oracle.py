@@ -287,7 +287,7 @@ def expand_block_mask(block_mask, n_q, n_kv, block=128):
 
 
 def dense_ext_backward_fp32(q, k, v, do, causal=False, softmax_scale=None, block_mask=None, dropout_p=0.0, seed=0,
-                            offset=0, q_row0=0, kv_col0=0):
+                            offset=0, q_row0=0, kv_col0=0, block=128):
     """fp32 forward + closed-form gradients of
         O = dropout(softmax(mask(Q K^T * scale))) V
     as the dense branch of the reference's stand-alone module computes it (src/fa3/torch/flashattention_pytorch.py:80-87:
@@ -304,7 +304,7 @@ def dense_ext_backward_fp32(q, k, v, do, causal=False, softmax_scale=None, block
         vis = visible_mask(n_q, n_kv, q_row0, kv_col0)
     vis = vis[None].expand(bh, n_q, n_kv)
     if block_mask is not None:
-        bm = expand_block_mask(block_mask.cpu(), n_q, n_kv)
+        bm = expand_block_mask(block_mask.cpu(), n_q, n_kv, block)
         vis = vis & (bm if bm.dim() == 3 else bm[None])
     s = s.masked_fill(~vis, NEG_INF)
     lse = torch.logsumexp(s, dim=-1)

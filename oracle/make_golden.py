@@ -41,6 +41,52 @@ CASES = [
 ]
 
 
+def block_sparse_golden():
+    """tests/golden/ref_block_sparse.npz: outputs of the reference's stand-alone attention module
+    (src/fa3/torch/flashattention_pytorch.py) in eval mode -- its block-sparse branch (`_block_sparse_flash_attention`,
+    :94-174) and its dense branch (:80-87) -- on the same q, k, v, so the oracle's masked attention
+    (dense_ext_backward_fp32 with dropout 0) is pinned to the reference's own numbers.  The module file imports
+    datasets / tiktoken at the top (not installed here), so only its `MultiHeadAttention` class is executed: the class
+    source is read from the reference tree and exec'd with torch / nn / math in scope (nothing is copied)."""
+    import math
+
+    from torch import nn
+
+    src = (REF / "src" / "fa3" / "torch" / "flashattention_pytorch.py").read_text()
+    start = src.index("class MultiHeadAttention(nn.Module):")
+    end = src.index("def look_ahead_mask_")
+    scope = {"torch": torch, "nn": nn, "math": math}
+    exec(compile(src[start:end], "flashattention_pytorch.py::MultiHeadAttention", "exec"), scope)
+    mha_cls = scope["MultiHeadAttention"]
+    arrays, cases = {}, []
+    for name, seed, (b, h, n, d), block in (("bs_a", 200, (1, 2, 64, 16), 16), ("bs_b", 201, (2, 2, 80, 32), 16),
+                                            ("bs_c", 202, (1, 1, 96, 64), 32)):
+        torch.manual_seed(seed)
+        q, k, v = (torch.randn(b, h, n, d) for _ in range(3))
+        nb = (n + block - 1) // block
+        bm = (torch.rand(nb, nb) < 0.5).to(torch.int32)
+        bm[torch.arange(nb), torch.arange(nb)] = 1  # every query block keeps its diagonal block
+        mod = mha_cls(d_model=h * d, num_heads=h, dropout=0.0, block_size=block).eval()
+        with torch.no_grad():
+            o_sparse = mod._block_sparse_flash_attention(q, k, v, 1.0, None, bm)
+            causal = torch.tril(torch.ones(n, n))[None, None]
+            o_sparse_causal = mod._block_sparse_flash_attention(q, k, v, 1.0, causal, bm)
+            # the dense branch, written out as the module does (:80-87) with the element mask the tiles imply
+            elem = bm.repeat_interleave(block, 0).repeat_interleave(block, 1)[:n, :n][None, None]
+            scores = torch.matmul(q, k.transpose(-2, -1)) / math.sqrt(d)
+            o_dense = torch.matmul(torch.softmax(scores.masked_fill(elem == 0, float("-inf")), dim=-1), v)
+        for key, t in (("q", q), ("k", k), ("v", v), ("block_mask", bm), ("o_sparse", o_sparse),
+                       ("o_sparse_causal", o_sparse_causal), ("o_dense_masked", o_dense)):
+            arrays[f"{name}/{key}"] = t.numpy()
+        cases.append({"name": name, "seed": seed, "shape": [b, h, n, d], "block": block})
+    np.savez_compressed(OUT / "ref_block_sparse.npz", **arrays)
+    (OUT / "ref_block_sparse.json").write_text(json.dumps({
+        "generator": "oracle/make_golden.py::block_sparse_golden", "torch": torch.__version__,
+        "reference_functions": ["fa3.torch.flashattention_pytorch.MultiHeadAttention._block_sparse_flash_attention (eval)"],
+        "cases": cases}, indent=1))
+    print(f"wrote ref_block_sparse.npz: {len(arrays)} arrays, {(OUT / 'ref_block_sparse.npz').stat().st_size / 1024:.0f} KiB")
+
+
 def main():
     sys.path.insert(0, str(REF / "src"))
     from common.correctness import reference_attention, reference_backward  # noqa: E402
@@ -91,6 +137,7 @@ def main():
         "cases": manifest}, indent=1))
     size = (OUT / "ref_vectors.npz").stat().st_size
     print(f"wrote {len(arrays)} arrays, {size / 1024:.0f} KiB")
+    block_sparse_golden()
 
 
 if __name__ == "__main__":
