@@ -465,12 +465,12 @@ def cast_scaled(acc: torch.Tensor, alpha: float, dtype: torch.dtype) -> torch.Te
 # ------------------------------------------------------------------------------------------------------------------
 # the six functions of the reference's pybind module
 # ------------------------------------------------------------------------------------------------------------------
-@torch.no_grad()  # reference csrc/fa2/fa2_fwd.cu:38 (NoGradGuard)
 def _pad4(x):
     d = x.shape[-1]
     return x.contiguous() if d % 4 == 0 else torch.nn.functional.pad(x, (0, 4 - d % 4)).contiguous()
 
 
+@torch.no_grad()  # reference csrc/fa2/fa2_fwd.cu:38 (NoGradGuard)
 def _forward(q, k, v, causal, softmax_scale):
     _validate_qkv(q, k, v)
     d = q.shape[-1]

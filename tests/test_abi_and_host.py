@@ -94,6 +94,53 @@ def test_argument_validation_happens_before_any_cuda_call():
     assert b"extras" in lib.fa_sm100_strerror(-9)
 
 
+def test_fp32_and_fp8_entries_validate_before_any_cuda_call():
+    import flashattention_lab_cuda as ext
+
+    lib = ext.load_library()
+    fake = ctypes.c_void_p(256)
+    f32 = dict(bh=1, n_q=8, n_kv=8, d=64, dtype_code=2, causal=False, softmax_scale=1.0)
+
+    def fwd32(**over):
+        s = ext.make_shape(**{**f32, **over})
+        return lib.fa_sm100_fwd_f32(ctypes.byref(s), fake, fake, fake, fake, fake, None)
+
+    assert fwd32(dtype_code=1) == -1          # the fp32 entries take fp32 only
+    assert fwd32(d=130) == -2 and fwd32(d=6) == -2 and fwd32(d=256) == -2
+    assert fwd32(n_kv=0) == -3
+    assert fwd32() <= -6                      # valid arguments: fails only on the missing device
+    s = ext.make_shape(**f32)
+    assert lib.fa_sm100_fwd_f32(ctypes.byref(s), None, fake, fake, fake, fake, None) == -4
+    assert lib.fa_sm100_bwd_f32(ctypes.byref(s), fake, fake, fake, fake, fake, fake, None, fake, fake, fake, None) == -4
+
+    q = lambda **kw: lib.fa_sm100_fp8_quantize(fake, fake, fake, kw.get("bh", 2), kw.get("n", 256), kw.get("d", 128),
+                                               kw.get("stride", 0), kw.get("dtype", 1), 1, 0, None)
+    assert q(dtype=2) == -1 and q(d=64) == -2 and q(n=0) == -3 and q(stride=100) == -3
+    assert q() <= -6
+    s8 = ext.make_shape(bh=1, n_q=256, n_kv=256, d=64, dtype_code=1, causal=True, softmax_scale=0.1)
+    assert lib.fa_sm100_fwd_fp8(ctypes.byref(s8), fake, fake, fake, fake, fake, fake, fake, fake, fake, None) == -2
+    with pytest.raises(NotImplementedError):
+        ext.fp8_quantize_raw(torch.zeros(1, 8, 64, dtype=torch.bfloat16), True)
+
+
+def test_block_mask_argument_checks():
+    import flashattention_lab_cuda as ext
+
+    ok, keep = ext._make_ext(torch.ones(2, 3, dtype=torch.bool), 4, 200, 300, 0.25, 7, 4)
+    assert keep.dtype == torch.uint8 and ok.mask_bh_stride == 0 and ok.seed == 7 and ok.offset == 4
+    per_slice, _ = ext._make_ext(torch.ones(4, 2, 3), 4, 200, 300, 0.0, 0, 0)
+    assert per_slice.mask_bh_stride == 6
+    with pytest.raises(RuntimeError):
+        ext._make_ext(torch.ones(3, 3), 4, 200, 300, 0.0, 0, 0)          # wrong tile grid
+    with pytest.raises(RuntimeError):
+        ext._make_ext(torch.ones(2, 2, 3), 4, 200, 300, 0.0, 0, 0)       # per-slice mask with the wrong slice count
+    with pytest.raises(RuntimeError):
+        ext._make_ext(torch.ones(6), 4, 200, 300, 0.0, 0, 0)
+    for p in (-0.1, 1.0):
+        with pytest.raises(ValueError):
+            ext._make_ext(None, 4, 200, 300, p, 0, 0)
+
+
 def test_shape_struct_layout_matches_header():
     import flashattention_lab_cuda as ext
 
