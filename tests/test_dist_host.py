@@ -144,11 +144,11 @@ def _gloo_worker(rank, world, port, causal, q, k, v, do, out_queue):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("causal", [False, True])
-def test_ring_attention_gloo_world2(causal):
-    world = 2
+@pytest.mark.parametrize("world,causal", [(2, False), (2, True), (3, True), (4, False)])
+def test_ring_attention_gloo(world, causal):
+    # world 2 has prev == next; 3 and 4 exercise distinct ring neighbours in the send/recv driver
     torch.manual_seed(2)
-    q, k, v, do = (torch.randn(2, 64, 16) for _ in range(4))
+    q, k, v, do = (torch.randn(2, 24 * world, 16) for _ in range(4))
     ctx = mp.get_context("spawn")
     queue = ctx.Queue()
     port = _free_port()
