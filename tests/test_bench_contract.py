@@ -69,6 +69,8 @@ def test_sweep_records_follow_the_reference_benchmark_schema(tmp_path):
     assert abs(fwd["tflops"] - 4.0 * 4 * 16 * 4096 ** 2 * 128 / 2e-3 / 1e12) < 1e-9  # no causal discount (reference)
     assert abs(both["tflops"] - 8.0 * 2 * 4 * 1024 ** 2 * 64 / 1e-3 / 1e12) < 1e-9 and both["fp8"] is False
     assert fwd["fp8"] is None and bad["tflops"] is None and bad["status"] == "unsupported"
+    f8 = sweep.make_record("fa3", "forward", "bf16", True, 4096, 128, 4, 16, 2.0, 0.1, 1.0, fp8=True)
+    assert f8["fp8"] is True and f8["method"].endswith(" FP8") and list(f8) == reference_fields  # compare_all's label
     sweep.write_results("t", [fwd, both, bad], tmp_path)
     rows = list(csv.DictReader((tmp_path / "t.csv").open()))
     assert list(rows[0]) == reference_fields and len(rows) == 3

@@ -50,14 +50,15 @@ def iter_causal_flags(args):  # reference benchmarks/bench_utils.py:267-272
 
 
 def make_record(algo, direction, dtype, causal, n, d, b, h, mean_ms, std_ms, peak_mb, status="ok", error=None,
-                algorithmic_tflops=None):
-    """One row in the reference's BenchmarkRecord schema."""
+                algorithmic_tflops=None, fp8=False):
+    """One row in the reference's BenchmarkRecord schema (method label with an " FP8" suffix as
+    benchmarks/bench_compare_all.py:65-67)."""
     factor = 4.0 if direction == "forward" else 8.0  # reference attention_flops (:210-215)
     tflops = None if mean_ms is None else factor * b * h * n * n * d / (mean_ms * 1e-3) / 1e12
-    return {"method": f"{algo.upper()} (sm_100a)", "algo": algo, "backend": "cuda", "direction": direction,
+    return {"method": f"{algo.upper()} (sm_100a)" + (" FP8" if fp8 else ""), "algo": algo, "backend": "cuda", "direction": direction,
             "dtype": dtype, "causal": bool(causal), "seqlen": n, "head_dim": d, "batch_size": b, "num_heads": h,
             "mean_ms": mean_ms, "std_ms": std_ms, "tflops": tflops, "peak_mem_mb": peak_mb, "status": status,
-            "fp8": False if algo == "fa3" else None,
+            "fp8": bool(fp8) if algo == "fa3" else None,
             "config": None if algorithmic_tflops is None else f"algorithmic_tflops={algorithmic_tflops:.1f}",
             "error": error}
 
@@ -88,8 +89,10 @@ def timeit(fn, warmup, iters):
     return mean, (sum((t - mean) ** 2 for t in ts) / len(ts)) ** 0.5
 
 
-def run_point(api_name, api, dtype_name, d, n, b, h, causal, warmup, iters):
+def run_point(api_name, api, dtype_name, d, n, b, h, causal, warmup, iters, fp8=False):
     import torch
+
+    extra = {"fp8": True} if fp8 else {}  # FA3 only: e4m3 forward, 16-bit straight-through backward
 
     dtype = getattr(torch, DTYPES[dtype_name])
     g = torch.Generator(device="cuda").manual_seed(0)
@@ -98,8 +101,8 @@ def run_point(api_name, api, dtype_name, d, n, b, h, causal, warmup, iters):
     f_fwd = 4.0 * b * h * n * n * d * (0.5 if causal else 1.0)
     torch.cuda.reset_peak_memory_stats()
     with torch.no_grad():
-        t_f, sd_f = timeit(lambda: api(q, k, v, causal=causal, backend="cuda"), warmup, iters)
-    o, _ = api(q, k, v, causal=causal, backend="cuda")
+        t_f, sd_f = timeit(lambda: api(q, k, v, causal=causal, backend="cuda", **extra), warmup, iters)
+    o, _ = api(q, k, v, causal=causal, backend="cuda", **extra)
 
     def bwd():
         torch.autograd.backward(o, do, retain_graph=True)
@@ -113,9 +116,9 @@ def run_point(api_name, api, dtype_name, d, n, b, h, causal, warmup, iters):
                "bwd_ms": None, "fwd_tflops": f_fwd / t_f / 1e9, "bwd_tflops": None, "fwd_bwd_tflops": None,
                "frac_nominal": None}
         recs = [make_record(api_name, "forward", dtype_name, causal, n, d, b, h, t_f, sd_f, peak_mb,
-                            algorithmic_tflops=row["fwd_tflops"]),
+                            algorithmic_tflops=row["fwd_tflops"], fp8=fp8),
                 make_record(api_name, "backward", dtype_name, causal, n, d, b, h, None, None, None, "unsupported",
-                            str(exc)[:200])]
+                            str(exc)[:200], fp8=fp8)]
         return row, recs
     peak_mb = torch.cuda.max_memory_allocated() / 2 ** 20
     row = {"api": api_name, "dtype": dtype_name, "d": d, "N": n, "B": b, "H": h, "causal": causal, "fwd_ms": t_f,
@@ -123,9 +126,9 @@ def run_point(api_name, api, dtype_name, d, n, b, h, causal, warmup, iters):
            "fwd_bwd_tflops": 3.5 * f_fwd / (t_f + t_b) / 1e9}
     row["frac_nominal"] = row["fwd_bwd_tflops"] / NOMINAL
     recs = [make_record(api_name, "forward", dtype_name, causal, n, d, b, h, t_f, sd_f, peak_mb,
-                        algorithmic_tflops=row["fwd_tflops"]),
+                        algorithmic_tflops=row["fwd_tflops"], fp8=fp8),
             make_record(api_name, "backward", dtype_name, causal, n, d, b, h, t_f + t_b, (sd_f ** 2 + sd_b ** 2) ** 0.5,
-                        peak_mb, algorithmic_tflops=row["fwd_bwd_tflops"])]
+                        peak_mb, algorithmic_tflops=row["fwd_bwd_tflops"], fp8=fp8)]
     return row, recs
 
 
@@ -135,7 +138,12 @@ def main():
     ap.add_argument("--algos", nargs="+", default=["fa1", "fa2", "fa3"], choices=["fa1", "fa2", "fa3"])
     ap.add_argument("--c3", action="store_true", help="BASELINE config C3 preset (overrides shapes / dtypes / algos)")
     ap.add_argument("--out", default=str(ROOT / "gpurun_out"), help="directory for <name>.json / <name>.csv")
-    ap.add_argument("--name", default="sweep_records")
+    ap.add_argument("--name", "--tag", dest="name", default="sweep_records",
+                    help="base name of the result files (--tag: reference benchmarks/bench_compare_all.py:81)")
+    ap.add_argument("--fp8", action="store_true",
+                    help="also run FA3 with fp8=True at every point (reference benchmarks/bench_compare_all.py:73)")
+    ap.add_argument("--directions", nargs="+", default=["forward", "backward"], choices=["forward", "backward"],
+                    help="which records to write (both are always timed; reference bench_compare_all.py:74-80)")
     args = ap.parse_args()
     import torch
     from fa1 import fa1_attention
@@ -144,34 +152,37 @@ def main():
 
     apis = {"fa1": fa1_attention, "fa2": fa2_attention, "fa3": fa3_attention}
     if args.c3:
-        points = [(a, dt, d, n, 16384 // n, 2048 // d, c) for a in ("fa1", "fa3") for dt in ("bf16", "fp16")
+        points = [(a, dt, d, n, 16384 // n, 2048 // d, c, False) for a in ("fa1", "fa3") for dt in ("bf16", "fp16")
                   for d in (128, 64) for n in (1024, 2048, 4096, 8192, 16384) for c in (True, False)]
         warmup, iters = 3, 10
     else:
-        points = [(a, dt, d, n, b, h, c) for a in args.algos for dt in args.dtypes for d in args.head_dim
-                  for n in args.seqlen for b in args.batch_size for h in args.num_heads for c in iter_causal_flags(args)]
+        points = [(a, dt, d, n, b, h, c, f8) for a in args.algos for dt in args.dtypes for d in args.head_dim
+                  for n in args.seqlen for b in args.batch_size for h in args.num_heads for c in iter_causal_flags(args)
+                  for f8 in ([False, True] if (a == "fa3" and args.fp8) else [False])]
         warmup, iters = args.warmup, args.iters
     rows, records = [], []
     print("| api | dtype | d | N | B | H | causal | fwd ms | fwd TF/s | bwd ms | bwd TF/s | fwd+bwd TF/s | % of 2250 |")
     print("|---|---|---|---|---|---|---|---|---|---|---|---|---|")
-    for api_name, dt, d, n, b, h, causal in points:
+    for api_name, dt, d, n, b, h, causal, fp8 in points:
+        label = api_name + ("+fp8" if fp8 else "")
         try:
-            row, recs = run_point(api_name, apis[api_name], dt, d, n, b, h, causal, warmup, iters)
+            row, recs = run_point(api_name, apis[api_name], dt, d, n, b, h, causal, warmup, iters, fp8=fp8)
         except (NotImplementedError, RuntimeError) as exc:  # unsupported point: recorded like the reference does
             oom = "out of memory" in str(exc).lower()
             status = "oom" if oom else "unsupported"
-            records += [make_record(api_name, direction, dt, causal, n, d, b, h, None, None, None, status, str(exc)[:200])
-                        for direction in ("forward", "backward")]
-            print(f"| {api_name} | {dt} | {d} | {n} | {b} | {h} | {causal} | - | - | - | - | {status} | - |", flush=True)
+            records += [make_record(api_name, direction, dt, causal, n, d, b, h, None, None, None, status, str(exc)[:200],
+                                    fp8=fp8) for direction in args.directions]
+            print(f"| {label} | {dt} | {d} | {n} | {b} | {h} | {causal} | - | - | - | - | {status} | - |", flush=True)
             torch.cuda.empty_cache()
             continue
+        row["api"] = label
         rows.append(row)
-        records += recs
+        records += [r for r in recs if r["direction"] in args.directions]
         if row["bwd_ms"] is None:
-            print(f"| {api_name} | {dt} | {d} | {n} | {b} | {h} | {causal} | {row['fwd_ms']:.3f} | {row['fwd_tflops']:.0f} | "
+            print(f"| {label} | {dt} | {d} | {n} | {b} | {h} | {causal} | {row['fwd_ms']:.3f} | {row['fwd_tflops']:.0f} | "
                   f"- | - | forward only | - |", flush=True)
             continue
-        print(f"| {api_name} | {dt} | {d} | {n} | {b} | {h} | {causal} | {row['fwd_ms']:.3f} | {row['fwd_tflops']:.0f} | "
+        print(f"| {label} | {dt} | {d} | {n} | {b} | {h} | {causal} | {row['fwd_ms']:.3f} | {row['fwd_tflops']:.0f} | "
               f"{row['bwd_ms']:.3f} | {row['bwd_tflops']:.0f} | {row['fwd_bwd_tflops']:.0f} | "
               f"{100 * row['frac_nominal']:.1f} |", flush=True)
     print("JSON " + json.dumps(rows))
