@@ -17,8 +17,6 @@ from __future__ import annotations
 
 from importlib import import_module
 
-import torch
-
 _EXT = None
 _EXT_NAMES = ("flashattention_lab_cuda", "flashattention_lab._C")
 

@@ -11,7 +11,7 @@ import torch.multiprocessing as mp
 from dist.ring import (BlockOps, contiguous_split, ring_attention, ring_backward, ring_forward, run_loopback,
                        zigzag_chunk_ids, zigzag_merge, zigzag_split)
 from dist.shard import shard_range, sharded_attention
-from oracle.attention_oracle import blocked_backward, blocked_forward, dense_backward_fp32, dense_forward, merge_partials
+from oracle.attention_oracle import blocked_backward, dense_backward_fp32, dense_forward, merge_partials
 
 
 # ---------------------------------------------------------------------------------------------------------------------

@@ -1,6 +1,6 @@
 """2-rank microbenchmark: bandwidth of the ring's block exchange primitives (NCCL batch_isend_irecv vs symmetric-memory
 peer copies).  torchrun --nproc-per-node 2 tools/p2p_bw.py"""
-import os, time
+import os
 import torch
 import torch.distributed as dist
 

@@ -1,6 +1,5 @@
 """Per-tensor parity report: max-abs, max-rel (|ref| > 1e-2), #violations at the reference tolerances
 (5e-2/5e-2 for 16-bit O/dQ/dK/dV, 1e-3 for LSE) of the sm_100a kernels against the CPU oracle on the same inputs."""
-import json
 import sys
 from pathlib import Path
 
