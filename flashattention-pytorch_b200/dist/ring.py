@@ -446,7 +446,9 @@ _checked_shapes = set()
 
 def _check_equal_across_ranks(q, group=None):
     """Every rank must own the same number of rows (the schedule slices received blocks at the LOCAL chunk size).
-    Checked once per (group, shape): one small all_gather."""
+    Checked once per (group, shape) with one small all_gather — not per call, because under NCCL that collective's
+    kernel would queue behind the SM-filling attention kernels of every step.  The cache assumes what the check then
+    establishes: all ranks of the group call with the same sequence of shapes."""
     import torch.distributed as dist
 
     if not dist.is_initialized():
@@ -465,7 +467,7 @@ def _check_equal_across_ranks(q, group=None):
 
 def ring_attention(q, k, v, causal=False, softmax_scale=None, group=None, ops: Optional[BlockOps] = None):
     """Sequence-parallel attention.  q, k, v: this rank's LOCAL rows, (bh, n_local, d) or (B, H, n_local, d), head dim
-    64 or 128; for ``causal=True`` they must be laid out zig-zag (``zigzag_split``).  Returns (o, lse) for the local
+    a multiple of 8 up to 128; for ``causal=True`` they must be laid out zig-zag (``zigzag_split``).  Returns (o, lse) for the local
     rows; differentiable."""
     if softmax_scale is None:
         softmax_scale = q.shape[-1] ** -0.5
