@@ -9,6 +9,14 @@ Parity status: PINNED.  ``tests/test_oracle_golden.py`` checks every function he
     ``oracle/make_golden.py`` and committed under ``tests/golden/``;
   * and, when present, the reference's csrc compiled for CPU (``oracle/_ref``, built by ``oracle/build_ref.py``).
 The reference holds no golden vectors of its own: its tests compute expectations on the fly.
+Round-2 additions and their pins:
+  * ``expand_block_mask`` / ``dense_ext_backward_fp32`` WITHOUT dropout: PINNED against outputs of the reference's
+    stand-alone block-sparse module (``tests/golden/ref_block_sparse.npz``, block sizes 32 and 64).
+  * dropout (``philox4x32_7`` / ``dropout_keep_mask``): PARITY UNPINNED against the reference — its dropout draws from
+    torch's global generator and its tiled branch drops un-normalised exponentials, so no bit pattern of it can be
+    reproduced.  The generator itself is pinned to the published Philox4x32-10 known-answer vectors.
+  * FP8 (``fp8_quantize_dequantize`` / ``fp8_forward_oracle``): PARITY UNPINNED against the reference — its fp8 emulation
+    is numerically broken; this oracle is fp32 attention on quantise -> dequantise inputs, defined here.
 
 Two restatements of the same operator, fp32 arithmetic on whatever dtype the inputs have (inputs are up-cast, as the
 reference does):
