@@ -17,6 +17,7 @@ Round-2 additions and their pins:
     reproduced.  The generator itself is pinned to the published Philox4x32-10 known-answer vectors.
   * FP8 (``fp8_quantize_dequantize`` / ``fp8_forward_oracle``): PARITY UNPINNED against the reference — its fp8 emulation
     is numerically broken; this oracle is fp32 attention on quantise -> dequantise inputs, defined here.
+    Only its per-block scales are pinned (= the reference's ``_block_absmax_scale`` / 448, ``ref_fp8_helpers.npz``).
 
 Two restatements of the same operator, fp32 arithmetic on whatever dtype the inputs have (inputs are up-cast, as the
 reference does):

@@ -87,6 +87,29 @@ def block_sparse_golden():
     print(f"wrote ref_block_sparse.npz: {len(arrays)} arrays, {(OUT / 'ref_block_sparse.npz').stat().st_size / 1024:.0f} KiB")
 
 
+def fp8_helpers_golden():
+    """tests/golden/ref_fp8_helpers.npz: the one piece of the reference's fp8 emulation that is sound on its own — the
+    per-block absolute maxima of `_block_absmax_scale` (src/fa3/torch/impl.py:20-31), ragged last block included.  The
+    oracle's per-block scales are these maxima / 448.  (The emulation's Hadamard step is not a Walsh-Hadamard transform
+    and its quantiser only clamps to [-1, 1] — SURVEY.md D5 — so nothing else of it can serve as a pin.)"""
+    sys.path.insert(0, str(REF / "src"))
+    from fa3.torch.impl import _block_absmax_scale  # noqa: E402
+
+    arrays, cases = {}, []
+    for name, seed, (bh, n, d), block in (("amax_a", 300, (2, 300, 128), 128), ("amax_b", 301, (3, 128, 128), 128),
+                                          ("amax_c", 302, (1, 77, 128), 128)):
+        torch.manual_seed(seed)
+        x = torch.randn(bh, n, d) * torch.rand(bh, n, 1) * 4.0
+        arrays[f"{name}/x"] = x.numpy()
+        arrays[f"{name}/block_absmax"] = _block_absmax_scale(x, block).numpy()
+        cases.append({"name": name, "seed": seed, "shape": [bh, n, d], "block": block})
+    np.savez_compressed(OUT / "ref_fp8_helpers.npz", **arrays)
+    (OUT / "ref_fp8_helpers.json").write_text(json.dumps({
+        "generator": "oracle/make_golden.py::fp8_helpers_golden", "torch": torch.__version__,
+        "reference_functions": ["fa3.torch.impl._block_absmax_scale"], "cases": cases}, indent=1))
+    print(f"wrote ref_fp8_helpers.npz: {len(arrays)} arrays")
+
+
 def main():
     sys.path.insert(0, str(REF / "src"))
     from common.correctness import reference_attention, reference_backward  # noqa: E402
@@ -138,6 +161,7 @@ def main():
     size = (OUT / "ref_vectors.npz").stat().st_size
     print(f"wrote {len(arrays)} arrays, {size / 1024:.0f} KiB")
     block_sparse_golden()
+    fp8_helpers_golden()
 
 
 if __name__ == "__main__":
